@@ -1,0 +1,495 @@
+"""torch.autograd Functions over the dv3b200 C ABI (include/dv3b200.h).
+
+PyTorch is plumbing here: it owns device memory, the current stream and autograd bookkeeping.  All
+arithmetic happens in csrc/*.cu.  Every function requires CUDA fp32 tensors and raises otherwise --
+there is no CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from ._lib import lib, Dv3Error
+
+MODE_GLU, MODE_HIGHWAY = 0, 1
+
+
+# ----------------------------------------------------------------------------------------------
+# plumbing
+# ----------------------------------------------------------------------------------------------
+def _chk(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise Dv3Error("dv3b200 ops need CUDA tensors (got %s); there is no CPU path" % t.device)
+        if t.dtype != torch.float32:
+            raise Dv3Error("dv3b200 ops are fp32 (got %s)" % t.dtype)
+        if not t.is_contiguous():
+            raise Dv3Error("dv3b200 ops need contiguous tensors")
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class DropoutState:
+    """Step seed in device memory + call-site salts.
+
+    keep(i) = f(seed[0], salt, i).  ``seed`` is an int64[1] device tensor: bump it once per training
+    step (``advance()`` is a device-side add, so it can live inside a captured CUDA graph); salts are
+    handed out in call order and must be reset at the start of every forward so that the backward (and
+    a graph replay) see the same sequence."""
+
+    def __init__(self):
+        self.seed = None
+        self.salt = 0
+
+    def seed_tensor(self, device):
+        if self.seed is None or self.seed.device != device:
+            self.seed = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64,
+                                     device=device)
+        return self.seed
+
+    def manual_seed(self, s, device):
+        self.seed = torch.tensor([int(s) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=device)
+
+    def next_salt(self):
+        self.salt += 1
+        return self.salt
+
+    def start_forward(self):
+        self.salt = 0
+
+    def advance(self):
+        if self.seed is not None:
+            self.seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+
+
+rng = DropoutState()
+
+
+def _drop_args(p, training, device):
+    """-> (p_eff, seed_ptr, salt) ; consumes a salt only when dropout is live."""
+    if training and p > 0.0:
+        return float(p), _p(rng.seed_tensor(device)), rng.next_salt()
+    return 0.0, None, 0
+
+
+# ----------------------------------------------------------------------------------------------
+# weight-norm packing helpers
+# ----------------------------------------------------------------------------------------------
+def _wn_conv_fwd(v, g):
+    """v (Cout, Cin, k), g (Cout,1,1) -> w_f [k][Cin][Cout], w_b [k][Cout][Cin], inv_norm [Cout]."""
+    Cout, Cin, k = v.shape
+    w_f = torch.empty(k, Cin, Cout, device=v.device, dtype=torch.float32)
+    w_b = torch.empty(k, Cout, Cin, device=v.device, dtype=torch.float32)
+    inv = torch.empty(Cout, device=v.device, dtype=torch.float32)
+    scale = torch.empty_like(inv)
+    lib.call("dv3_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(w_f), _p(w_b), Cout, Cin, k,
+             1, Cout, Cin * Cout, Cin, 1, Cout * Cin, _stream())
+    return w_f, w_b, inv
+
+
+def _wn_bwd(partials, nsplit, v, g, inv):
+    dv = torch.empty_like(v)
+    dg = torch.empty_like(g)
+    R = v.shape[0]
+    X = v.numel() // R
+    lib.call("dv3_weightnorm_bwd", _p(partials), v.numel(), nsplit, _p(v), _p(g), _p(inv), _p(dv),
+             _p(dg), R, X, 1, _stream())
+    return dv, dg
+
+
+def _wgrad_conv(dab, x, v_shape, k, dilation, causal, p, seed_ptr, salt):
+    """partials [nsplit][Cout*Cin*k] in v's layout (Cout, Cin, k)."""
+    B, M, T = dab.shape
+    Cin = x.shape[1]
+    nsplit = lib.raw("dv3_conv1d_wgrad_nsplit")(B, M, Cin, T, k)
+    numel = M * Cin * k
+    partials = torch.empty(nsplit, numel, device=x.device, dtype=torch.float32)
+    lib.call("dv3_conv1d_wgrad", _p(dab), _p(x), _p(partials), numel, B, M, Cin, T, k, dilation,
+             int(causal), p, seed_ptr, salt, M, Cin * k, 0, k, 1, _stream())
+    return partials, nsplit
+
+
+# ----------------------------------------------------------------------------------------------
+# fused ConvBlock (Conv1dGLU / HighwayConv1d)
+# ----------------------------------------------------------------------------------------------
+class _ConvBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, v, g, bias, spk, k, dilation, causal, mode, residual, p_drop, training):
+        _chk(x, v, g, bias, spk)
+        B, C, T = x.shape
+        assert v.shape == (2 * C, C, k), "ConvBlock needs in_channels == out_channels"
+        w_f, w_b, inv = _wn_conv_fwd(v, g)
+        p, seed_ptr, salt = _drop_args(p_drop, training, x.device)
+        need_bwd = any(ctx.needs_input_grad)
+        y = torch.empty_like(x)
+        a = torch.empty_like(x) if need_bwd else None
+        s = torch.empty_like(x) if need_bwd else None
+        lib.call("dv3_convblock_fwd", _p(x), _p(w_f), _p(bias), _p(spk), _p(y), _p(a), _p(s), B, C, T, k,
+                 dilation, int(causal), mode, int(residual), p, seed_ptr, salt, _stream())
+        if need_bwd:
+            ctx.save_for_backward(x, v, g, a, s, w_b, inv)
+            ctx.cfg = (k, dilation, causal, mode, residual, p, salt, spk is not None, x.device)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, v, g, a, s, w_b, inv = ctx.saved_tensors
+        k, dilation, causal, mode, residual, p, salt, has_spk, dev = ctx.cfg
+        seed_ptr = _p(rng.seed_tensor(dev)) if p > 0 else None
+        dy = _c(dy)
+        B, C, T = x.shape
+        dab = torch.empty(B, 2 * C, T, device=dev, dtype=torch.float32)
+        dbias = torch.zeros(2 * C, device=dev, dtype=torch.float32)
+        lib.call("dv3_convblock_gate_bwd", _p(dy), _p(a), _p(s), _p(x), _p(dab), _p(dbias), B, C, T, mode,
+                 int(residual), _stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if mode == MODE_GLU:
+                addmode, e1, e2, alpha = (1, dy, None, 0.7071067811865476) if residual else (0, None, None, 0.0)
+            else:
+                addmode, e1, e2, alpha = 2, dy, s, 0.0
+            lib.call("dv3_conv1d_dgrad", _p(dab), _p(w_b), _p(dx), B, 2 * C, C, T, k, dilation,
+                     int(causal), p, seed_ptr, salt, addmode, _p(e1), _p(e2), alpha, _stream())
+        dv = dg = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            partials, nsplit = _wgrad_conv(dab, x, v.shape, k, dilation, causal, p, seed_ptr, salt)
+            dv, dg = _wn_bwd(partials, nsplit, v, g, inv)
+        dspk = dab[:, :C, :] if has_spk and ctx.needs_input_grad[4] else None
+        return dx, dv, dg, dbias, dspk, None, None, None, None, None, None, None
+
+
+def convblock(x, v, g, bias, spk=None, k=3, dilation=1, causal=False, mode=MODE_GLU, residual=True,
+              p_drop=0.0, training=False):
+    """Fused weight-normed dilated conv + gate.  x (B,C,T); v (2C,C,k); g (2C,1,1); bias (2C);
+    spk (B,C,T) already softsign'ed (or None)."""
+    return _ConvBlockFn.apply(_c(x), v, g, bias, None if spk is None else _c(spk), int(k), int(dilation),
+                              bool(causal), int(mode), bool(residual), float(p_drop), bool(training))
+
+
+# ----------------------------------------------------------------------------------------------
+# plain weight-normed Conv1d (+ReLU)
+# ----------------------------------------------------------------------------------------------
+class _Conv1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, v, g, bias, k, dilation, causal, relu):
+        _chk(x, v, g, bias)
+        B, Cin, T = x.shape
+        Cout = v.shape[0]
+        assert v.shape == (Cout, Cin, k)
+        w_f, w_b, inv = _wn_conv_fwd(v, g)
+        y = torch.empty(B, Cout, T, device=x.device, dtype=torch.float32)
+        lib.call("dv3_conv1d_fwd", _p(x), _p(w_f), _p(bias), _p(y), B, Cin, Cout, T, k, dilation,
+                 int(causal), int(relu), _stream())
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x, v, g, w_b, inv, y if relu else None)
+            ctx.cfg = (k, dilation, causal, relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, v, g, w_b, inv, y = ctx.saved_tensors
+        k, dilation, causal, relu = ctx.cfg
+        dy = _c(dy)
+        B, Cin, T = x.shape
+        Cout = v.shape[0]
+        dbias = torch.zeros(Cout, device=x.device, dtype=torch.float32)
+        dyr = torch.empty_like(dy) if relu else dy
+        lib.call("dv3_bias_act_bwd", _p(dy), _p(y), _p(dyr), _p(dbias), B, Cout, T, int(relu), _stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            lib.call("dv3_conv1d_dgrad", _p(dyr), _p(w_b), _p(dx), B, Cout, Cin, T, k, dilation, int(causal),
+                     0.0, None, 0, 0, None, None, 0.0, _stream())
+        dv = dg = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            partials, nsplit = _wgrad_conv(dyr, x, v.shape, k, dilation, causal, 0.0, None, 0)
+            dv, dg = _wn_bwd(partials, nsplit, v, g, inv)
+        return dx, dv, dg, dbias, None, None, None, None
+
+
+def conv1d(x, v, g, bias, k=1, dilation=1, causal=False, relu=False):
+    """Weight-normed Conv1d with 'same' (or causal) padding, optional fused ReLU.  x (B,Cin,T)."""
+    return _Conv1dFn.apply(_c(x), v, g, bias, int(k), int(dilation), bool(causal), bool(relu))
+
+
+# ----------------------------------------------------------------------------------------------
+# layout, lookups, position encodings, dropout
+# ----------------------------------------------------------------------------------------------
+class _TransposeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _chk(x)
+        B, R, C = x.shape
+        y = torch.empty(B, C, R, device=x.device, dtype=torch.float32)
+        lib.call("dv3_transpose", _p(x), _p(y), B, R, C, _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        B, C, R = dy.shape
+        dx = torch.empty(B, R, C, device=dy.device, dtype=torch.float32)
+        lib.call("dv3_transpose", _p(dy), _p(dx), B, C, R, _stream())
+        return dx
+
+
+def transpose12(x):
+    """(B, R, C) -> contiguous (B, C, R) -- the (B,T,C) <-> (B,C,T) layout change."""
+    return _TransposeFn.apply(_c(x))
+
+
+_err_flags = {}
+
+
+def _err_flag(device):
+    f = _err_flags.get(device)
+    if f is None:
+        f = torch.zeros(1, dtype=torch.int32, device=device)
+        _err_flags[device] = f
+    return f
+
+
+def check_index_errors(device=None):
+    """Raise if any lookup kernel saw an out-of-range id since the last call (one D2H sync)."""
+    for dev, f in _err_flags.items():
+        if device is not None and dev != device:
+            continue
+        if int(f.item()) != 0:
+            f.zero_()
+            raise IndexError("dv3b200: embedding / position index out of range")
+
+
+class _EmbeddingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, table, padding_idx):
+        _chk(table)
+        assert ids.dtype == torch.int64 and ids.is_cuda
+        ids = ids.contiguous()
+        N, (V, D) = ids.numel(), table.shape
+        out = torch.empty(*ids.shape, D, device=table.device, dtype=torch.float32)
+        lib.call("dv3_embedding_fwd", _p(ids), _p(table), _p(out), N, D, V, _p(_err_flag(table.device)),
+                 _stream())
+        ctx.save_for_backward(ids)
+        ctx.cfg = (V, D, -1 if padding_idx is None else int(padding_idx))
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ids,) = ctx.saved_tensors
+        V, D, pad = ctx.cfg
+        dy = _c(dy)
+        dtable = torch.zeros(V, D, device=dy.device, dtype=torch.float32)
+        lib.call("dv3_embedding_bwd", _p(ids), _p(dy), _p(dtable), ids.numel(), D, V, pad, _stream())
+        return None, dtable, None
+
+
+def embedding(ids, table, padding_idx=None):
+    return _EmbeddingFn.apply(ids, table, padding_idx)
+
+
+class _SinusoidFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, table, w):
+        _chk(table, w)
+        assert pos.dtype == torch.int64 and pos.is_cuda and pos.dim() == 2
+        pos = pos.contiguous()
+        B, T = pos.shape
+        P, D = table.shape
+        out = torch.empty(B, T, D, device=table.device, dtype=torch.float32)
+        lib.call("dv3_sinusoid_fwd", _p(pos), _p(table), _p(w), w.numel(), _p(out), B, T, D, P,
+                 _p(_err_flag(table.device)), _stream())
+        ctx.save_for_backward(pos, table, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        pos, table, w = ctx.saved_tensors
+        dy = _c(dy)
+        B, T = pos.shape
+        P, D = table.shape
+        dtable = torch.zeros_like(table) if ctx.needs_input_grad[1] else None
+        dw = torch.zeros_like(w) if ctx.needs_input_grad[2] else None
+        if dtable is not None or dw is not None:
+            lib.call("dv3_sinusoid_bwd", _p(pos), _p(table), _p(w), w.numel(), _p(dy), _p(dtable), _p(dw), B, T,
+                     D, P, _stream())
+        return None, dtable, dw
+
+
+def sinusoidal_encoding(pos, table, w):
+    """pos int64 (B,T); table (P,D) raw position table; w fp32 tensor with 1 or B position rates."""
+    return _SinusoidFn.apply(pos, table, w)
+
+
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed_t, salt):
+        _chk(x)
+        y = torch.empty_like(x)
+        lib.call("dv3_dropout", _p(x), _p(y), x.numel(), p, _p(seed_t), salt, _stream())
+        ctx.cfg = (p, seed_t, salt)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed_t, salt = ctx.cfg
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        lib.call("dv3_dropout", _p(dy), _p(dx), dy.numel(), p, _p(seed_t), salt, _stream())
+        return dx, None, None, None
+
+
+def dropout(x, p, training):
+    if not training or p <= 0.0:
+        return x
+    return _DropoutFn.apply(_c(x), float(p), rng.seed_tensor(x.device), rng.next_salt())
+
+
+# ----------------------------------------------------------------------------------------------
+# ConvTranspose1d(k=2, stride=2) and Linear on the conv kernels
+# ----------------------------------------------------------------------------------------------
+class _ConvT2Fn(torch.autograd.Function):
+    """y[b,co,2t+j] = bias[co] + sum_ci x[b,ci,t] w[ci,co,j]; w = g*v/||v|| over dim 0 (= Cin).
+    Runs as a 1x1 conv with 2*Cout output rows ordered (j,co) followed by a time interleave."""
+
+    @staticmethod
+    def forward(ctx, x, v, g, bias):
+        _chk(x, v, g, bias)
+        B, Cin, T = x.shape
+        Cout = v.shape[1]
+        assert v.shape == (Cin, Cout, 2)
+        dev = x.device
+        w_f = torch.empty(Cin, 2 * Cout, device=dev, dtype=torch.float32)     # [ci][(j,co)]
+        w_b = torch.empty(2 * Cout, Cin, device=dev, dtype=torch.float32)     # [(j,co)][ci]
+        inv = torch.empty(Cin, device=dev, dtype=torch.float32)
+        scale = torch.empty_like(inv)
+        lib.call("dv3_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(w_f), _p(w_b), Cin, Cout, 2,
+                 2 * Cout, 1, Cout, 1, Cin, Cout * Cin, _stream())
+        bias2 = bias.repeat(2)
+        yp = torch.empty(B, 2 * Cout, T, device=dev, dtype=torch.float32)
+        lib.call("dv3_conv1d_fwd", _p(x), _p(w_f), _p(bias2), _p(yp), B, Cin, 2 * Cout, T, 1, 1, 0, 0, _stream())
+        y = torch.empty(B, Cout, 2 * T, device=dev, dtype=torch.float32)
+        lib.call("dv3_interleave2", _p(yp), _p(y), B, Cout, T, 0, _stream())
+        ctx.save_for_backward(x, v, g, w_b, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, v, g, w_b, inv = ctx.saved_tensors
+        dy = _c(dy)
+        B, Cin, T = x.shape
+        Cout = v.shape[1]
+        dev = x.device
+        dyp = torch.empty(B, 2 * Cout, T, device=dev, dtype=torch.float32)
+        lib.call("dv3_interleave2", _p(dy), _p(dyp), B, Cout, T, 1, _stream())
+        db2 = torch.zeros(2 * Cout, device=dev, dtype=torch.float32)
+        lib.call("dv3_bias_act_bwd", _p(dyp), None, None, _p(db2), B, 2 * Cout, T, 0, _stream())
+        dbias = db2[:Cout] + db2[Cout:]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            lib.call("dv3_conv1d_dgrad", _p(dyp), _p(w_b), _p(dx), B, 2 * Cout, Cin, T, 1, 1, 0, 0.0, None, 0, 0,
+                     None, None, 0.0, _stream())
+        dv = dg = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            M = 2 * Cout
+            nsplit = lib.raw("dv3_conv1d_wgrad_nsplit")(B, M, Cin, T, 1)
+            numel = v.numel()
+            partials = torch.empty(nsplit, numel, device=dev, dtype=torch.float32)
+            # element (m=(j,co), ci) -> v layout (ci, co, j): co*2 + j + ci*Cout*2
+            lib.call("dv3_conv1d_wgrad", _p(dyp), _p(x), _p(partials), numel, B, M, Cin, T, 1, 1, 0, 0.0, None, 0,
+                     Cout, 2, 1, Cout * 2, 0, _stream())
+            dv, dg = _wn_bwd(partials, nsplit, v, g, inv)
+        return dx, dv, dg, dbias
+
+
+def conv_transpose1d_k2s2(x, v, g, bias):
+    return _ConvT2Fn.apply(_c(x), v, g, bias)
+
+
+def linear(x, v, g, bias):
+    """Weight-normed Linear over the last dim (reference modules.py:80-85): x (..., Cin) -> (..., Cout).
+    Runs on the conv kernels in channel-major layout: (N,Cin) -> (1,Cin,N) -> 1x1 conv -> back."""
+    shp = x.shape
+    Cin, Cout = shp[-1], v.shape[0]
+    x2 = x.reshape(1, -1, Cin)
+    y = conv1d(transpose12(x2), v.view(Cout, Cin, 1), g.view(Cout, 1, 1), bias)
+    return transpose12(y).reshape(*shp[:-1], Cout)
+
+
+# ----------------------------------------------------------------------------------------------
+# attention core (channel-major): q (B,E,Td), k (B,E,Ts), v (B,E,Ts) -> out (B,E,Td), probs (B,Td,Ts)
+# ----------------------------------------------------------------------------------------------
+def _bgemm(A, sA, Bm, sB, C, sCb, ldc, batch, M, N, K, alpha=1.0, accumulate=False):
+    lib.call("dv3_bgemm", _p(A), sA[0], sA[1], sA[2], _p(Bm), sB[0], sB[1], sB[2], _p(C), sCb, ldc, batch, M, N,
+             K, float(alpha), int(accumulate), _stream())
+
+
+class _AttentionCoreFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, mask, p_drop, training):
+        _chk(q, k, v)
+        B, E, Td = q.shape
+        Ts = k.shape[2]
+        dev = q.device
+        scores = torch.empty(B, Td, Ts, device=dev, dtype=torch.float32)
+        # S[t,s] = sum_e q[e,t] k[e,s]                       (reference deepvoice3.py:143, no 1/sqrt(d))
+        _bgemm(q, (E * Td, 1, Td), k, (E * Ts, Ts, 1), scores, Td * Ts, Ts, B, Td, Ts, E)
+        p, seed_ptr, salt = _drop_args(p_drop, training, dev)
+        probs = torch.empty_like(scores)
+        pd = torch.empty_like(scores) if p > 0 else None
+        lib.call("dv3_softmax_fwd", _p(scores), _p(mask), _p(probs), _p(pd), B * Td, Ts, Td, p, seed_ptr, salt,
+                 _stream())
+        pv = pd if pd is not None else probs
+        scale = Ts * (1.0 / Ts) ** 0.5                         # deepvoice3.py:170-171
+        out = torch.empty(B, E, Td, device=dev, dtype=torch.float32)
+        # O[e,t] = scale * sum_s v[e,s] pd[t,s]
+        _bgemm(v, (E * Ts, Ts, 1), pv, (Td * Ts, 1, Ts), out, E * Td, Td, B, E, Td, Ts, alpha=scale)
+        ctx.save_for_backward(q, k, v, probs, pd)
+        ctx.cfg = (p, salt, scale)
+        ctx.mark_non_differentiable()
+        return out, probs
+
+    @staticmethod
+    def backward(ctx, dout, dprobs_ext):
+        q, k, v, probs, pd = ctx.saved_tensors
+        p, salt, scale = ctx.cfg
+        B, E, Td = q.shape
+        Ts = k.shape[2]
+        dev = q.device
+        dout = _c(dout)
+        seed_ptr = _p(rng.seed_tensor(dev)) if p > 0 else None
+        pv = pd if pd is not None else probs
+        # dPd[t,s] = scale * sum_e dO[e,t] v[e,s]
+        dpd = torch.empty(B, Td, Ts, device=dev, dtype=torch.float32)
+        _bgemm(dout, (E * Td, 1, Td), v, (E * Ts, Ts, 1), dpd, Td * Ts, Ts, B, Td, Ts, E, alpha=scale)
+        # dV[e,s] = scale * sum_t dO[e,t] pd[t,s]
+        dv = torch.empty_like(v)
+        _bgemm(dout, (E * Td, Td, 1), pv, (Td * Ts, Ts, 1), dv, E * Ts, Ts, B, E, Ts, Td, alpha=scale)
+        ds = torch.empty_like(dpd)
+        dpe = _c(dprobs_ext) if dprobs_ext is not None else None
+        lib.call("dv3_softmax_bwd", _p(probs), _p(dpd), _p(dpe), _p(ds), B * Td, Ts, p, seed_ptr, salt, _stream())
+        # dq[e,t] = sum_s k[e,s] dS[t,s] ; dk[e,s] = sum_t q[e,t] dS[t,s]
+        dq = torch.empty_like(q)
+        _bgemm(k, (E * Ts, Ts, 1), ds, (Td * Ts, 1, Ts), dq, E * Td, Td, B, E, Td, Ts)
+        dk = torch.empty_like(k)
+        _bgemm(q, (E * Td, Td, 1), ds, (Td * Ts, Ts, 1), dk, E * Ts, Ts, B, E, Ts, Td)
+        return dq, dk, dv, None, None, None
+
+
+def attention_core(q, k, v, mask=None, p_drop=0.0, training=False):
+    """mask: (B, Ts) uint8/bool, 1 = padding.  Returns (out (B,E,Td), probs (B,Td,Ts))."""
+    if mask is not None:
+        mask = mask.to(torch.uint8).contiguous()
+    return _AttentionCoreFn.apply(_c(q), _c(k), _c(v), mask, float(p_drop), bool(training))

@@ -1,0 +1,125 @@
+/* dv3b200 -- C ABI of the B200-native hot path of r9y9/deepvoice3_pytorch.
+ *
+ * The reference has no FFI of its own (it is pure Python on ATen): the seam it offers is the Python
+ * module API (deepvoice3_pytorch.builder.* -> nn.Module).  This header is the
+ * C-ABI layer underneath our mirror of that API; each entry point names the reference code whose GPU
+ * work (ATen/cuDNN/cuBLAS calls) it replaces.  See INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; dv3_last_error() gives the message of the
+ *     most recent failure on the calling thread.  No exceptions, no torch types.
+ *   - all pointers are caller-owned DEVICE memory (fp32 unless stated), densely packed, row-major with the
+ *     last index fastest; kernels never allocate.  `stream` is a cudaStream_t; every call is asynchronous on
+ *     it and re-entrant (no global mutable state besides cached device attributes).
+ *   - activations use the reference's conv layout (B, C, T), T fastest.
+ *   - dropout: keep(i) is a pure function of (*seed_ptr, salt, element index i); `seed_ptr` points to 8
+ *     bytes of device memory (so a captured CUDA graph gets fresh masks by bumping it), `salt` identifies the
+ *     call site.  p_drop == 0 or seed_ptr == NULL disables it.
+ *   - tensors must have fewer than 2^31 elements.
+ */
+#ifndef DV3B200_H
+#define DV3B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* dv3_last_error(void);
+int dv3_abi_version(void);
+
+/* ---- weight normalisation: reference modules.py:85,100,109 (nn.utils.weight_norm pre-hook) -------------
+ * v is [R][X][k] (k fastest), g is [R]; w = g*v/||v[r]||.  Writes w in up to two packed layouts:
+ * out1[r*s1r + x*s1x + j*s1j] and out2[r*s2r + x*s2x + j*s2j] (either may be NULL).
+ * inv_norm, scale: [R] outputs (1/||v||, g/||v||), inv_norm is needed by the backward. */
+int dv3_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* scale, float* out1,
+                       float* out2, int R, int X, int k, long long s1r, long long s1x, long long s1j,
+                       long long s2r, long long s2x, long long s2j, void* stream);
+/* dw_partials: [nsplit][R*X*k] partial gradients w.r.t. w in v's own layout (summed here);
+ * outputs dv [R][X][k], dg [R]. */
+int dv3_weightnorm_bwd(const float* dw_partials, long long split_stride, int nsplit, const float* v,
+                       const float* g, const float* inv_norm, float* dv, float* dg, int R, int X, int k,
+                       void* stream);
+
+/* ---- fused ConvBlock forward: reference modules.py:145-164 (Conv1dGLU._forward, mode 0) and
+ * modules.py:200-226 (HighwayConv1d._forward, mode 1).
+ * x (B,C,T); w_f packed [k][C][2C]; bias [2C]; spk (B,C,T) = softsign(speaker_proj(.)) transposed, or NULL;
+ * y (B,C,T); save_a / save_s (B,C,T) = gate pre-activation a(+bias+spk) and sigmoid(b) for the backward, or NULL.
+ * causal: left pad (k-1)*dilation; else symmetric (k-1)/2*dilation. Dropout is applied to the conv input only. */
+int dv3_convblock_fwd(const float* x, const float* w_f, const float* bias, const float* spk, float* y,
+                      float* save_a, float* save_s, int B, int C, int T, int k, int dilation, int causal,
+                      int mode, int residual, float p_drop, const unsigned long long* seed_ptr,
+                      unsigned salt, void* stream);
+/* gate backward: dab (B,2C,T) = [d a ; d b], dbias[2C] += row sums (may be NULL). x only read in mode 1. */
+int dv3_convblock_gate_bwd(const float* dy, const float* a, const float* s, const float* x, float* dab,
+                           float* dbias, int B, int C, int T, int mode, int residual, void* stream);
+
+/* ---- plain weight-normed Conv1d (+ fused ReLU): reference conv.py:7-15 via modules.py:94-100.
+ * x (B,Cin,T); w_f packed [k][Cin][Cout]; y (B,Cout,T). */
+int dv3_conv1d_fwd(const float* x, const float* w_f, const float* bias, float* y, int B, int Cin, int Cout,
+                   int T, int k, int dilation, int causal, int relu, void* stream);
+/* data gradient of a conv with M output rows: dx (B,Cin,T) = mask * convT(dab (B,M,T), w_b [k][M][Cin]) + addend.
+ * mask = the forward's input-dropout mask (same seed/salt).  addmode 0: none; 1: + alpha*e1; 2: + e1*(1-e2)
+ * (e1, e2 (B,Cin,T)) -- the residual-path gradients of the GLU / highway blocks. */
+int dv3_conv1d_dgrad(const float* dab, const float* w_b, float* dx, int B, int M, int Cin, int T, int k,
+                     int dilation, int causal, float p_drop, const unsigned long long* seed_ptr,
+                     unsigned salt, int addmode, const float* e1, const float* e2, float alpha,
+                     void* stream);
+/* weight gradient, split over (b,t): writes dv3_conv1d_wgrad_nsplit(...) partials of `split_stride` floats each;
+ * element (m, ci, j) of a partial lives at (m%msplit)*s_m + (m/msplit)*s_mh + ci*s_n + j*s_j. */
+int dv3_conv1d_wgrad_nsplit(int B, int M, int Cin, int T, int k);
+int dv3_conv1d_wgrad(const float* dab, const float* x, float* dw_partials, long long split_stride, int B,
+                     int M, int Cin, int T, int k, int dilation, int causal, float p_drop,
+                     const unsigned long long* seed_ptr, unsigned salt, int msplit, int s_m, int s_mh,
+                     int s_n, int s_j, void* stream);
+/* dyr = relu ? dy*(y>0) : (untouched); dbias[C] += sum_{b,t} dyr.  dy,y,dyr (B,C,T). */
+int dv3_bias_act_bwd(const float* dy, const float* y, float* dyr, float* dbias, int B, int C, int T,
+                     int relu, void* stream);
+
+/* ---- layout change (B,R,C) -> (B,C,R): every x.transpose(1,2) between the attention (B,T,C) and conv (B,C,T)
+ * layouts, reference deepvoice3.py:86,93,318,324,340-345,355,359,592,602; nyanko.py:66,206,214-217,230,234,402. */
+int dv3_transpose(const float* in, float* out, int B, int R, int C, void* stream);
+
+/* ---- embedding lookup: reference deepvoice3.py:74, nyanko.py:64,201-203,__init__.py:69-71 (F.embedding).
+ * ids int64 [N] -> out (N,D); an id outside [0,V) sets *err_flag (device int) to 1 and writes nothing.
+ * bwd: dtable[ids[n]] += dy[n] except rows == padding_idx (pass -1 for none); dtable must be pre-zeroed. */
+int dv3_embedding_fwd(const long long* ids, const float* table, float* out, int N, int D, int V, int* err_flag,
+                      void* stream);
+int dv3_embedding_bwd(const long long* ids, const float* dy, float* dtable, int N, int D, int V,
+                      long long padding_idx, void* stream);
+
+/* ---- sinusoidal position encoding: reference modules.py:27-31,45-64 (SinusoidalEncoding.forward).
+ * pos int64 (B,T) in [0,P); table (P,D) raw (non-sinusoidal) table; w [nw] position rate(s), nw in {1,B};
+ * out (B,T,D).  bwd accumulates into pre-zeroed dtable (P,D) and dw [nw] (either may be NULL). */
+int dv3_sinusoid_fwd(const long long* pos, const float* table, const float* w, int nw, float* out, int B, int T,
+                     int D, int P, int* err_flag, void* stream);
+int dv3_sinusoid_bwd(const long long* pos, const float* table, const float* w, int nw, const float* dy,
+                     float* dtable, float* dw, int B, int T, int D, int P, void* stream);
+
+/* ---- standalone dropout y = x*mask/(1-p): reference F.dropout at deepvoice3.py:75,80,294,321,588,597.
+ * Calling it on the gradient with the same (seed, salt) is the backward. */
+int dv3_dropout(const float* x, float* y, long long n, float p, const unsigned long long* seed_ptr, unsigned salt,
+                void* stream);
+
+/* ---- masked row softmax + dropout: reference deepvoice3.py:145-148,161-165.
+ * s (rows,L); mask (rows/rows_per_b, L) bytes, 1 = padding (-inf), or NULL; probs = softmax (the returned
+ * alignment); pd = dropout(probs) (may be NULL).  bwd: ds = P*(g - <g,P>), g = dpd*dropmask + dprobs_ext. */
+int dv3_softmax_fwd(const float* s, const unsigned char* mask, float* probs, float* pd, int rows, int L,
+                    int rows_per_b, float p, const unsigned long long* seed_ptr, unsigned salt, void* stream);
+int dv3_softmax_bwd(const float* probs, const float* dpd, const float* dprobs_ext, float* ds, int rows, int L,
+                    float p, const unsigned long long* seed_ptr, unsigned salt, void* stream);
+
+/* ---- ConvTranspose1d(k=2,s=2) time interleave: reference deepvoice3.py:519,527; nyanko.py:372,377.
+ * in (B,2C,T) rows ordered (j,co) -> out (B,C,2T), out[b,co,2t+j] = in[b,j*C+co,t]; inverse=1 undoes it. */
+int dv3_interleave2(const float* in, float* out, int B, int C, int T, int inverse, void* stream);
+
+/* ---- batched strided GEMM C[b] = alpha*A_b*B_b (+C): the attention contractions, reference
+ * deepvoice3.py:143 (bmm(q,k)), :167 (bmm(p,v)) and their gradients.  A_b(m,k)=A[b*sAb+m*sAm+k*sAk],
+ * B_b(k,n)=B[b*sBb+k*sBk+n*sBn], C_b(m,n)=C[b*sCb+m*ldc+n]; each operand needs one unit stride. */
+int dv3_bgemm(const float* A, long long sAb, long long sAm, long long sAk, const float* B, long long sBb,
+              long long sBk, long long sBn, float* C, long long sCb, int ldc, int batch, int M, int N, int K,
+              float alpha, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DV3B200_H */
