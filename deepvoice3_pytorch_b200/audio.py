@@ -1,0 +1,139 @@
+"""Audio front-end with the reference's function names (reference audio.py): ``spectrogram(y)`` and
+``melspectrogram(y)`` take a float waveform and return (n_freq, n_frames) arrays in [0, 1] -- computed by ONE fused
+GPU pass (csrc/stft.cu) instead of two CPU lws STFTs.  ``stft_mel_batch`` is the batched device API the
+preprocessors should use (a whole shard of clips per launch; one H2D, one D2H).
+
+Out of scope (reference audio.py:37-43): ``inv_spectrogram`` / LWS phase recovery -- inference-only vocoding.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import lib, Dv3Error
+
+
+class _HP:
+    """Defaults of reference hparams.py / presets/*.json; override by assigning attributes."""
+    sample_rate = 22050
+    fft_size = 1024
+    hop_size = 256
+    num_mels = 80
+    fmin = 125
+    fmax = 7600
+    preemphasis = 0.97
+    min_level_db = -100
+    ref_level_db = 20
+
+
+hparams = _HP()
+_basis_cache = {}
+
+
+def _hz_to_mel(f):
+    f = np.asarray(f, dtype=np.float64)
+    lin = f / (200.0 / 3)
+    return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-10) / 1000.0) / (np.log(6.4) / 27.0), lin)
+
+
+def _mel_to_hz(m):
+    m = np.asarray(m, dtype=np.float64)
+    return np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), (200.0 / 3) * m)
+
+
+def _build_mel_basis():
+    """Slaney-scale, area-normalised triangular filterbank = librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax)
+    (reference audio.py:71-76); (num_mels, fft_size//2+1) float32."""
+    hp = hparams
+    if hp.fmax is not None:
+        assert hp.fmax <= hp.sample_rate // 2
+    n_bins = 1 + hp.fft_size // 2
+    freqs = np.linspace(0, hp.sample_rate / 2.0, n_bins)
+    edges = _mel_to_hz(np.linspace(_hz_to_mel(hp.fmin), _hz_to_mel(hp.fmax or hp.sample_rate / 2.0),
+                                   hp.num_mels + 2))
+    basis = np.zeros((hp.num_mels, n_bins))
+    for m in range(hp.num_mels):
+        lo, ce, hi = edges[m], edges[m + 1], edges[m + 2]
+        up = (freqs - lo) / (ce - lo)
+        down = (hi - freqs) / (hi - ce)
+        basis[m] = np.maximum(0.0, np.minimum(up, down)) * (2.0 / (hi - lo))
+    return basis.astype(np.float32)
+
+
+def _device_basis(device):
+    hp = hparams
+    key = (str(device), hp.sample_rate, hp.fft_size, hp.num_mels, hp.fmin, hp.fmax)
+    if key not in _basis_cache:
+        basis = _build_mel_basis()
+        nz = basis > 0
+        start = np.array([int(np.argmax(r)) if r.any() else 0 for r in nz], dtype=np.int32)
+        length = np.array([int(len(r) - np.argmax(r[::-1]) - s) if r.any() else 0
+                           for r, s in zip(nz, start)], dtype=np.int32)
+        _basis_cache[key] = (torch.from_numpy(basis).to(device), torch.from_numpy(start).to(device),
+                             torch.from_numpy(length).to(device))
+    return _basis_cache[key]
+
+
+def num_frames(n_samples):
+    return lib.raw("dv3_stft_num_frames")(int(n_samples))
+
+
+def stft_mel_batch(wav, lengths=None, want_linear=True, want_mel=True):
+    """wav: (nclips, max_len) fp32 CUDA tensor; lengths: int32 CUDA tensor (nclips) or None (= all max_len).
+    -> linear (nclips, max_frames, 513), mel (nclips, max_frames, num_mels) in the stored (T, F) layout."""
+    if not (torch.is_tensor(wav) and wav.is_cuda and wav.dtype == torch.float32 and wav.dim() == 2):
+        raise Dv3Error("stft_mel_batch needs a (nclips, max_len) fp32 CUDA tensor; there is no CPU path")
+    if hparams.fft_size != 1024 or hparams.hop_size != 256:
+        raise Dv3Error("the fused kernel is built for fft_size=1024, hop_size=256 (every reference preset)")
+    wav = wav.contiguous()
+    nclips, max_len = wav.shape
+    dev = wav.device
+    if lengths is None:
+        lengths = torch.full((nclips,), max_len, dtype=torch.int32, device=dev)
+    lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
+    max_frames = num_frames(max_len)
+    basis, start, length = _device_basis(dev)
+    lin = torch.zeros(nclips, max_frames, hparams.fft_size // 2 + 1, device=dev) if want_linear else None
+    mel = torch.zeros(nclips, max_frames, hparams.num_mels, device=dev) if want_mel else None
+
+    def p(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+    lib.call("dv3_stft_mel", p(wav), p(lengths), p(basis), p(start), p(length), p(lin), p(mel), nclips, max_len,
+             max_frames, hparams.num_mels, float(hparams.preemphasis), float(hparams.min_level_db),
+             float(hparams.ref_level_db), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    return lin, mel
+
+
+def _single(y, want_linear, want_mel):
+    y = torch.as_tensor(np.asarray(y, dtype=np.float32)).view(1, -1).cuda()
+    lin, mel = stft_mel_batch(y, None, want_linear, want_mel)
+    return lin, mel
+
+
+def spectrogram(y):
+    """(fft_size//2+1, n_frames) normalised dB magnitude -- reference audio.py:31-34."""
+    lin, _ = _single(y, True, False)
+    return lin[0].t().cpu().numpy()
+
+
+def melspectrogram(y):
+    """(num_mels, n_frames) normalised dB mel spectrogram -- reference audio.py:46-51."""
+    _, mel = _single(y, False, True)
+    return mel[0].t().cpu().numpy()
+
+
+def _amp_to_db(x):
+    min_level = np.exp(hparams.min_level_db / 20 * np.log(10))
+    return 20 * np.log10(np.maximum(min_level, x))
+
+
+def _db_to_amp(x):
+    return np.power(10.0, x * 0.05)
+
+
+def _normalize(S):
+    return np.clip((S - hparams.min_level_db) / -hparams.min_level_db, 0, 1)
+
+
+def _denormalize(S):
+    return (np.clip(S, 0, 1) * -hparams.min_level_db) + hparams.min_level_db

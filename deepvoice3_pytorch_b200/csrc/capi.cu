@@ -13,7 +13,11 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+unsigned long long launch_count() { return g_launches; }
+
 int check_launch(const char* what) {
+    __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) return 0;
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -24,4 +28,5 @@ int check_launch(const char* what) {
 extern "C" {
 const char* dv3_last_error(void) { return dv3::g_err; }
 int dv3_abi_version(void) { return 1; }
+long long dv3_launch_count(void) { return (long long)dv3::launch_count(); }
 }

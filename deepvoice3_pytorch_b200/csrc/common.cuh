@@ -8,7 +8,8 @@ namespace dv3 {
 
 // ---- error plumbing (no exceptions across the C ABI) -------------------------------------------
 void set_error(const char* fmt, ...);
-int check_launch(const char* what);     // cudaGetLastError() -> 0 / error code, records message
+int check_launch(const char* what);     // counts the launch; cudaGetLastError() -> 0 / error code + message
+unsigned long long launch_count();
 
 #define DV3_REQUIRE(cond, ...)                                    \
     do {                                                          \

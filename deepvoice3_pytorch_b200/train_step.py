@@ -1,0 +1,273 @@
+"""One data-parallel training step of the hot path, B200-first.
+
+What the reference does per step (train.py:621-779) -- H2D of the batch, model forward, the four losses,
+backward, ``clip_grad_norm_``, ``Adam.step`` -- restated around three ideas:
+
+* **flat arenas**: every trainable parameter is a view into one contiguous fp32 buffer and every gradient a view
+  into another, so the optimizer (clip + Adam) is two kernel launches over ~26 M floats and the data-parallel
+  exchange is ONE NCCL all-reduce of the gradient arena over NVLink (the path is straight data-parallel over
+  utterances: no other collective exists);
+* **no host synchronisation inside the step**: the clip coefficient, learning rate and dropout seed live in
+  device memory, the loss is returned as a device scalar;
+* **graph capture**: because of the above the whole step (forward, loss, backward, optimizer) can be captured
+  once in a CUDA graph and replayed, which removes the ~1.5 k kernel-launch / autograd dispatch overhead that
+  dominates once the convolutions run on tensor cores.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import ops
+from ._lib import lib
+
+
+def noam_learning_rate_decay(init_lr, global_step, warmup_steps=4000):
+    """reference lrschedule.py:5-11."""
+    warmup_steps = float(warmup_steps)
+    step = global_step + 1.0
+    return init_lr * warmup_steps ** 0.5 * min(step * warmup_steps ** -1.5, step ** -0.5)
+
+
+def sequence_mask(lengths, max_len):
+    """(B,) int64 device tensor -> (B, max_len) float mask (reference train.py:261-271)."""
+    return (torch.arange(max_len, device=lengths.device)[None, :] < lengths[:, None]).float()
+
+
+def guided_attention_mask(input_lengths, target_lengths, max_target_len, max_input_len, g):
+    """W[b,t,n] = 1 - exp(-(n/N_b - t/T_b)^2 / (2 g^2)) inside (T_b, N_b), 0 outside -- computed on the device
+    from the two length vectors (the reference builds it with numba on the host and uploads it every step,
+    train.py:585-601, 734-738)."""
+    dev = input_lengths.device
+    N = input_lengths.double()[:, None, None]
+    T = target_lengths.double()[:, None, None]
+    n = torch.arange(max_input_len, device=dev, dtype=torch.float64)[None, None, :]
+    t = torch.arange(max_target_len, device=dev, dtype=torch.float64)[None, :, None]
+    W = 1.0 - torch.exp(-(n / N - t / T) ** 2 / (2 * g * g))
+    W = W * (n < N) * (t < T)
+    return W.float()
+
+
+def spec_loss(y_hat, y, mask, masked_loss_weight, binary_divergence_weight, eps=1e-8):
+    """reference train.py:547-582 with priority_freq_weight = 0 (the presets' value)."""
+    w = masked_loss_weight
+    l1 = (y_hat - y).abs().mean()
+    if w > 0:
+        mask_ = mask.expand_as(y_hat)
+        l1 = w * ((y_hat * mask_ - y * mask_).abs().sum() / mask_.sum()) + (1 - w) * l1
+    if binary_divergence_weight <= 0:
+        return l1, y_hat.new_zeros(())
+    logits = torch.log(y_hat + eps) - torch.log(1 - y_hat + eps)
+    z = -y * logits + torch.log1p(torch.exp(logits))
+    if w > 0:
+        mask_ = mask.expand_as(z)
+        bd = w * ((z * mask_).sum() / mask_.sum()) + (1 - w) * z.mean()
+    else:
+        bd = z.mean()
+    return l1, bd
+
+
+def training_loss(outs, batch, r=1, downsample_step=4, masked_loss_weight=0.5, binary_divergence_weight=0.1,
+                  guided_attention_sigma=0.2, use_guided_attention=True):
+    """Total loss of one step with seq2seq and postnet trained jointly (reference train.py:665-740)."""
+    mel_out, lin_out, attn, done_hat = outs
+    mel, y, done = batch["mel"], batch["y"], batch["done"]
+    tl = batch["target_lengths"]
+    dec_mask = tgt_mask = None
+    if masked_loss_weight > 0:
+        dec_mask = sequence_mask(tl // (r * downsample_step), mel.size(1)).unsqueeze(-1)
+        tgt_mask = sequence_mask(tl, y.size(1)).unsqueeze(-1) if downsample_step > 1 else dec_mask
+        dec_mask, tgt_mask = dec_mask[:, r:, :], tgt_mask[:, r:, :]
+    w = binary_divergence_weight
+    l1, bd = spec_loss(mel_out[:, :-r, :], mel[:, r:, :], dec_mask, masked_loss_weight, w)
+    loss = (1 - w) * l1 + w * bd
+    loss = loss + F.binary_cross_entropy(done_hat, done)
+    l1, bd = spec_loss(lin_out[:, :-r, :], y[:, r:, :], tgt_mask, masked_loss_weight, w)
+    loss = loss + (1 - w) * l1 + w * bd
+    if use_guided_attention:
+        soft = guided_attention_mask(batch["input_lengths_dev"], tl // r // downsample_step, attn.size(-2),
+                                     attn.size(-1), guided_attention_sigma)
+        loss = loss + (attn * soft).mean()
+    return loss
+
+
+class ParameterArena:
+    """Re-homes the trainable parameters of ``model`` into one flat fp32 buffer (and their gradients into
+    another).  ``state_dict`` / ``load_state_dict`` keep working: parameters stay nn.Parameters, only their
+    storage moves."""
+
+    def __init__(self, model, params=None):
+        params = list(model.get_trainable_parameters()) if params is None else list(params)
+        assert all(p.is_cuda and p.dtype == torch.float32 for p in params), "model must be on the GPU"
+        self.params = params
+        offs, n = [], 0
+        for p in params:
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4            # keep every view 16-byte aligned
+        self.numel = n
+        dev = params[0].device
+        self.flat = torch.zeros(n, device=dev)
+        self.grad = torch.zeros(n, device=dev)
+        for p, o in zip(params, offs):
+            self.flat[o:o + p.numel()].view_as(p).copy_(p.data)
+            p.data = self.flat[o:o + p.numel()].view_as(p)
+            p.grad = self.grad[o:o + p.numel()].view_as(p)
+        self.offsets = offs
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+
+class FlatAdam:
+    """torch.optim.Adam(betas, eps) + clip_grad_norm_(clip) over a ParameterArena in two launches."""
+
+    def __init__(self, arena, lr=5e-4, betas=(0.5, 0.9), eps=1e-6, clip_thresh=0.1):
+        self.arena = arena
+        self.lr, self.betas, self.eps, self.clip = lr, betas, eps, clip_thresh
+        dev = arena.flat.device
+        self.m = torch.zeros_like(arena.flat)
+        self.v = torch.zeros_like(arena.flat)
+        self.hyper = torch.zeros(4, device=dev)
+        # ring of pinned staging slots: the host may run several steps ahead of the stream, so a slot is only
+        # rewritten after the copy that last read it has completed (event wait, normally already signalled)
+        self._slots = [torch.zeros(4).pin_memory() for _ in range(4)]
+        self._events = [None] * 4
+        self.sumsq = torch.zeros(1, device=dev)
+        self.t = 0
+
+    def set_hyper(self, lr, grad_scale=1.0):
+        """Host-side scalar prep; the async H2D copy of 16 bytes is the only thing the stream sees."""
+        self.t += 1
+        b1, b2 = self.betas
+        i = self.t % 4
+        if self._events[i] is not None:
+            self._events[i].synchronize()
+        h = self._slots[i]
+        h[0], h[1], h[2], h[3] = lr, 1.0 - b1 ** self.t, 1.0 - b2 ** self.t, grad_scale
+        self.hyper.copy_(h, non_blocking=True)
+        self._events[i] = torch.cuda.Event()
+        self._events[i].record()
+
+    def apply(self):
+        """Device-only part (graph-capturable): grad norm -> clip -> Adam."""
+        a = self.arena
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.sumsq.zero_()
+        lib.call("dv3_sumsq", ctypes.c_void_p(a.grad.data_ptr()), a.numel, ctypes.c_void_p(self.sumsq.data_ptr()), st)
+        lib.call("dv3_adam_clip", ctypes.c_void_p(a.flat.data_ptr()), ctypes.c_void_p(a.grad.data_ptr()),
+                 ctypes.c_void_p(self.m.data_ptr()), ctypes.c_void_p(self.v.data_ptr()), a.numel,
+                 ctypes.c_void_p(self.hyper.data_ptr()), ctypes.c_void_p(self.sumsq.data_ptr()),
+                 self.betas[0], self.betas[1], self.eps, float(self.clip), st)
+
+    def grad_norm(self):
+        return self.sumsq.sqrt() * self.hyper[3]
+
+
+class TrainStep:
+    """model + losses + flat optimizer (+ NCCL gradient all-reduce when torch.distributed is initialised)."""
+
+    def __init__(self, model, init_lr=5e-4, betas=(0.5, 0.9), eps=1e-6, clip_thresh=0.1, r=1, downsample_step=4,
+                 masked_loss_weight=0.5, binary_divergence_weight=0.1, guided_attention_sigma=0.2,
+                 use_guided_attention=True, lr_schedule=noam_learning_rate_decay, use_graph=False):
+        self.model = model
+        self.arena = ParameterArena(model)
+        self.opt = FlatAdam(self.arena, init_lr, betas, eps, clip_thresh)
+        self.init_lr, self.lr_schedule = init_lr, lr_schedule
+        self.loss_kw = dict(r=r, downsample_step=downsample_step, masked_loss_weight=masked_loss_weight,
+                            binary_divergence_weight=binary_divergence_weight,
+                            guided_attention_sigma=guided_attention_sigma,
+                            use_guided_attention=use_guided_attention)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.global_step = 0
+        self.use_graph = use_graph
+        self._graph = None
+        self._static = None
+        self._loss = None
+        self.launches_per_step = None       # dv3 kernel launches inside one captured step (graph mode)
+
+    # -- pieces -------------------------------------------------------------------------------
+    def _forward_backward(self, batch):
+        self.arena.zero_grad()
+        outs = self.model(batch["x"], batch["mel"], speaker_ids=batch.get("speaker_ids"),
+                          text_positions=batch["text_positions"], frame_positions=batch["frame_positions"],
+                          input_lengths=batch["input_lengths_dev"])
+        loss = training_loss(outs, batch, **self.loss_kw)
+        loss.backward()
+        return loss.detach()
+
+    def _exchange_and_update(self):
+        if self.world > 1:
+            dist.all_reduce(self.arena.grad)            # sum; the 1/world average is folded into hyper[3]
+        self.opt.apply()
+        ops.rng.advance()                               # fresh dropout masks next step (device-side add)
+
+    # -- public -------------------------------------------------------------------------------
+    def step(self, batch):
+        """batch: dict of DEVICE tensors (x, text_positions, frame_positions int64; mel, y, done fp32;
+        target_lengths, input_lengths_dev int64) + host numpy ``input_lengths``.  Returns the loss (device)."""
+        self.model.train()
+        lr = self.lr_schedule(self.init_lr, self.global_step) if self.lr_schedule else self.init_lr
+        self.opt.set_hyper(lr, 1.0 / self.world)
+        if not self.use_graph:
+            loss = self._forward_backward(batch)
+            self._exchange_and_update()
+        else:
+            loss = self._graph_step(batch)
+        self.global_step += 1
+        return loss
+
+    def _graph_step(self, batch):
+        if self._graph is None:
+            # static input buffers; warm up on a side stream, then capture forward+loss+backward (+update when
+            # there is no collective to run in between)
+            self._static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._forward_backward(self._static)
+            torch.cuda.current_stream().wait_stream(s)
+            self._graph = torch.cuda.CUDAGraph()
+            n0 = lib.raw("dv3_launch_count")()
+            with torch.cuda.graph(self._graph):
+                self._loss = self._forward_backward(self._static)
+                if self.world == 1:
+                    self._exchange_and_update()
+            self.launches_per_step = int(lib.raw("dv3_launch_count")() - n0) + (2 if self.world > 1 else 0)
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                self._static[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        if self.world > 1:
+            self._exchange_and_update()
+        return self._loss
+
+
+def make_synthetic_batch(B=16, T_text=128, T_mel=800, downsample_step=4, r=1, n_speakers=1, n_vocab=149,
+                         mel_dim=80, linear_dim=513, seed=1234, pin=False):
+    """Synthetic batch of SURVEY.md section 8(d), on the HOST (what collate_fn would hand to the step)."""
+    gen = torch.Generator().manual_seed(seed)
+    T_dec = T_mel // downsample_step // r
+    b = {
+        "x": torch.randint(2, n_vocab, (B, T_text), generator=gen),
+        "text_positions": torch.arange(1, T_text + 1)[None, :].repeat(B, 1),
+        "frame_positions": torch.arange(1, T_dec + 1)[None, :].repeat(B, 1),
+        "mel": torch.rand(B, T_dec, mel_dim * r, generator=gen),
+        "y": torch.rand(B, T_mel, linear_dim, generator=gen),
+        "done": torch.cat([torch.zeros(B, T_dec - 1, 1), torch.ones(B, 1, 1)], dim=1),
+        "target_lengths": torch.full((B,), T_mel, dtype=torch.int64),
+        "input_lengths_dev": torch.full((B,), T_text, dtype=torch.int64),
+    }
+    if n_speakers > 1:
+        b["speaker_ids"] = torch.randint(0, n_speakers, (B,), generator=gen)
+    if pin:
+        b = {k: v.pin_memory() for k, v in b.items()}
+    b["input_lengths"] = np.full(B, T_text, dtype=np.int64)
+    return b
+
+
+def to_device(batch, device, non_blocking=True):
+    return {k: (v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v) for k, v in batch.items()}

@@ -26,6 +26,8 @@ extern "C" {
 
 const char* dv3_last_error(void);
 int dv3_abi_version(void);
+/* number of kernels this library has launched in this process (every launch is counted once) */
+long long dv3_launch_count(void);
 
 /* ---- weight normalisation: reference modules.py:85,100,109 (nn.utils.weight_norm pre-hook) -------------
  * v is [R][X][k] (k fastest), g is [R]; w = g*v/||v[r]||.  Writes w in up to two packed layouts:
@@ -118,6 +120,25 @@ int dv3_interleave2(const float* in, float* out, int B, int C, int T, int invers
 int dv3_bgemm(const float* A, long long sAb, long long sAm, long long sAk, const float* B, long long sBb,
               long long sBk, long long sBn, float* C, long long sCb, int ldc, int batch, int M, int N, int K,
               float alpha, int accumulate, void* stream);
+
+/* ---- optimizer step over a flat fp32 arena: reference train.py:756-759 (clip_grad_norm_ + Adam.step).
+ * dv3_sumsq: out[0] += sum(x^2) (zero it first).  dv3_adam_clip: g' = g*hyper[3]*min(1, max_norm/(||g*hyper[3]||+1e-6))
+ * (max_norm <= 0: no clipping), then torch.optim.Adam's update with lr=hyper[0], bias corrections hyper[1], hyper[2].
+ * hyper (4 floats) and sumsq live in device memory: no host sync, graph-replayable. */
+int dv3_sumsq(const float* x, long long n, float* out, void* stream);
+int dv3_adam_clip(float* p, const float* g, float* m, float* v, long long n, const float* hyper,
+                  const float* sumsq, float beta1, float beta2, float eps, float max_norm, void* stream);
+
+/* ---- fused STFT -> linear + mel front-end: reference audio.py:31-34 (spectrogram) and :46-51 (melspectrogram)
+ * incl. preemphasis (:21-23), lws sqrt-Hann STFT 1024/256 with 768-sample zero padding (:54-55), mel basis product
+ * (:64-68), dB (:79-81) and normalisation (:88-89).  wav (nclips, max_len) fp32; lengths int32 [nclips];
+ * mel_basis (n_mels, 513) dense with mel_start/mel_len [n_mels] giving each filter's non-zero span;
+ * linear (nclips, max_frames, 513) and mel (nclips, max_frames, n_mels) -- the transposed (T, F) layout the
+ * preprocessors store (ljspeech.py:72-73); either output may be NULL.  Frames >= a clip's own count are untouched. */
+int dv3_stft_num_frames(int n_samples);
+int dv3_stft_mel(const float* wav, const int* lengths, const float* mel_basis, const int* mel_start,
+                 const int* mel_len, float* linear, float* mel, int nclips, int max_len, int max_frames,
+                 int n_mels, float preemph, float min_level_db, float ref_level_db, void* stream);
 
 #ifdef __cplusplus
 }

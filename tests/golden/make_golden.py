@@ -270,6 +270,25 @@ def conv_ramp_case():
     fx.save("conv_ramp.npz")
 
 
+def init_fingerprints():
+    """Same torch seed -> same initial weights: per-tensor (sum, abs-sum, first element) of the reference
+    builders' freshly initialised models at the three BASELINE.json presets (seed 4321)."""
+    from deepvoice3_pytorch import builder
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_gpu_models import preset_kwargs
+    fx = Fixture()
+    for preset in ["deepvoice3_ljspeech", "nyanko_ljspeech", "deepvoice3_vctk"]:
+        bname, kw = preset_kwargs(preset)
+        torch.manual_seed(4321)
+        sd = getattr(builder, bname)(dropout=0.05, **kw).state_dict()
+        fx.put(preset, "meta", "keys", np.array(list(sd.keys())))
+        fx.put(preset, "meta", "shapes", np.array([str(tuple(v.shape)) for v in sd.values()]))
+        fx.put(preset, "out", "fingerprint", np.array(
+            [[float(v.double().sum()), float(v.double().abs().sum()), float(v.flatten()[0])]
+             for v in sd.values()]))
+    fx.save("init_fingerprints.npz")
+
+
 if __name__ == "__main__":
     tmp = import_reference()
     try:
@@ -277,5 +296,6 @@ if __name__ == "__main__":
         block_cases()
         model_cases()
         conv_ramp_case()
+        init_fingerprints()
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

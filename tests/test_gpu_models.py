@@ -1,0 +1,145 @@
+"""GPU parity of the full models (builder API) against the golden vectors of the live reference and,
+at the BASELINE.json preset sizes, against the CPU oracle.  rtol=1e-3 / atol=1e-4 (north_star)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as G
+from test_gpu_blocks import close, grad_close
+
+pytestmark = pytest.mark.gpu
+MODELS = G.load("models.npz")
+
+
+def _build(kw):
+    from deepvoice3_pytorch_b200 import builder
+    kw = dict(kw)
+    name = kw.pop("builder")
+    return getattr(builder, name)(**kw)
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+def test_model_golden(name):
+    case = MODELS[name]
+    model = _build(G.kwargs_of(case)).cuda()
+    missing = model.load_state_dict(G.tensors(case["sd"]), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model.train()          # dropout=0 in the fixture configs
+    ins = G.tensors(case["in"], "cuda")
+    ins["mel"].requires_grad_(True)
+    outs = model(ins["text"], ins["mel"], speaker_ids=ins.get("speaker_ids"),
+                 text_positions=ins["text_positions"], frame_positions=ins["frame_positions"],
+                 input_lengths=case["meta"]["input_lengths"])
+    for i, o in enumerate(outs):
+        close(o, case["out"][str(i)], what="%s out%d" % (name, i))
+    loss = sum((o * G.loss_weights(o.shape, i, "cuda")).sum() for i, o in enumerate(outs))
+    loss.backward()
+    params = dict(model.named_parameters())
+    for k, ref in case["gsd"].items():
+        assert params[k].grad is not None, k
+        grad_close(params[k].grad, ref, what="%s grad %s" % (name, k))
+    grad_close(ins["mel"].grad, case["gin"]["mel"], what="grad mel")
+    from deepvoice3_pytorch_b200 import ops
+    ops.check_index_errors()
+
+
+def preset_kwargs(name):
+    """The train.py:812-840 hparams -> builder kwargs mapping for the three BASELINE.json presets."""
+    base = dict(n_vocab=149, mel_dim=80, linear_dim=513, r=1, downsample_step=4, padding_idx=0, kernel_size=3,
+                use_memory_mask=True, trainable_positional_encodings=False, force_monotonic_attention=True,
+                use_decoder_state_for_postnet_input=True, freeze_embedding=False, window_ahead=3,
+                window_backward=1, speaker_embed_dim=16)
+    if name == "deepvoice3_ljspeech":
+        return "deepvoice3", dict(base, n_speakers=1, embed_dim=256, encoder_channels=512, decoder_channels=256,
+                                  converter_channels=256, max_positions=512, key_projection=True,
+                                  value_projection=True, speaker_embedding_weight_std=0.01)
+    if name == "nyanko_ljspeech":
+        return "nyanko", dict(base, n_speakers=1, embed_dim=128, encoder_channels=256, decoder_channels=256,
+                              converter_channels=256, max_positions=512, key_projection=False,
+                              value_projection=False, speaker_embedding_weight_std=0.01)
+    if name == "deepvoice3_vctk":
+        return "deepvoice3_multispeaker", dict(base, n_speakers=108, embed_dim=256, encoder_channels=512,
+                                               decoder_channels=256, converter_channels=256, max_positions=1024,
+                                               key_projection=True, value_projection=True,
+                                               speaker_embedding_weight_std=0.05)
+    raise ValueError(name)
+
+
+def synthetic_batch(B, T_text, T_dec, n_speakers, seed, ragged=True):
+    gen = torch.Generator().manual_seed(seed)
+    text = torch.randint(2, 149, (B, T_text), generator=gen)
+    lengths = torch.randint(T_text // 2, T_text + 1, (B,), generator=gen).numpy() if ragged \
+        else np.full(B, T_text)
+    lengths[0] = T_text
+    tpos = torch.arange(1, T_text + 1)[None].repeat(B, 1)
+    for b in range(B):
+        text[b, lengths[b]:] = 0
+        tpos[b, lengths[b]:] = 0
+    mel = torch.rand(B, T_dec, 80, generator=gen)
+    fpos = torch.arange(1, T_dec + 1)[None].repeat(B, 1)
+    spk = torch.randint(0, n_speakers, (B,), generator=gen) if n_speakers > 1 else None
+    return text, mel, tpos, fpos, lengths, spk
+
+
+@pytest.mark.parametrize("preset,B", [("deepvoice3_ljspeech", 4), ("nyanko_ljspeech", 2), ("deepvoice3_vctk", 3)])
+def test_preset_model_vs_oracle(preset, B):
+    """Full-width preset model, T_text=128, T_mel=800 (T_dec=200): forward + every parameter gradient."""
+    from deepvoice3_pytorch_b200 import builder
+    from oracle import dv3_oracle as O
+    from oracle.specs import spec_from_builder
+    bname, kw = preset_kwargs(preset)
+    kw["dropout"] = 0.0
+    torch.manual_seed(11)
+    model = getattr(builder, bname)(**kw)
+    with torch.no_grad():       # move g / bias off their init so the fixtures exercise them
+        gen = torch.Generator().manual_seed(5)
+        for n, p in model.named_parameters():
+            if n.endswith("weight_g"):
+                p.mul_(1 + 0.1 * torch.randn(p.shape, generator=gen))
+            elif n.endswith("bias"):
+                p.add_(0.05 * torch.randn(p.shape, generator=gen))
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    text, mel, tpos, fpos, lengths, spk = synthetic_batch(B, 128, 200, kw["n_speakers"], 77)
+
+    # CPU oracle: fp32 (the reference's arithmetic) and fp64 (the error yardstick), all parameters as leaves
+    spec = spec_from_builder(bname, **kw)
+
+    def run_oracle(dtype):
+        leaves = {k: (v.detach().to(dtype).requires_grad_(True) if v.is_floating_point() else v)
+                  for k, v in sd.items()}
+        outs_o = O.model_forward(leaves, spec, text, mel.to(dtype), spk, tpos, fpos, lengths)
+        loss_o = sum((o * G.loss_weights(o.shape, i, dtype=dtype)).sum() / o.numel() ** 0.5
+                     for i, o in enumerate(outs_o))
+        loss_o.backward()
+        return outs_o, {k: v.grad for k, v in leaves.items() if torch.is_tensor(v) and v.grad is not None}
+
+    outs_ref, grads32 = run_oracle(torch.float32)
+    _, grads64 = run_oracle(torch.float64)
+
+    model = model.cuda().train()
+    outs = model(text.cuda(), mel.cuda(), speaker_ids=None if spk is None else spk.cuda(),
+                 text_positions=tpos.cuda(), frame_positions=fpos.cuda(), input_lengths=lengths)
+    names = ["mel", "linear", "alignments", "done"]
+    for i, (o, r) in enumerate(zip(outs, outs_ref)):
+        assert o.shape == r.shape
+        close(o, r, what="%s %s" % (preset, names[i]))
+    loss = sum((o * G.loss_weights(o.shape, i, "cuda")).sum() / o.numel() ** 0.5 for i, o in enumerate(outs))
+    loss.backward()
+    # Gradients of the first layers sum thousands of terms through ~30 blocks, so two fp32 implementations
+    # differ by their accumulated round-off: measure both against the fp64 oracle and require ours to be no
+    # worse than 2e-3 of the tensor's max, or 3x the error the CPU fp32 restatement itself makes.
+    worst = 0.0
+    for k, p in model.named_parameters():
+        if k not in grads64:
+            continue
+        assert p.grad is not None, k
+        truth = grads64[k]
+        scale = float(truth.abs().max()) + 1e-12
+        err = float((p.grad.cpu().double() - truth).abs().max()) / scale
+        err32 = float((grads32[k].double() - truth).abs().max()) / scale
+        worst = max(worst, err)
+        assert err < max(2e-3, 3 * err32), "%s: rel-to-max gradient error %.3e (cpu fp32: %.3e)" % (k, err, err32)
+    print("worst relative-to-max gradient error vs fp64: %.3e" % worst)

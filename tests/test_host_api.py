@@ -1,0 +1,107 @@
+"""CPU-only checks of the host side: the C-ABI library exports what include/dv3b200.h declares, the builder
+API mirrors the reference (keys, shapes, seed-for-seed initialisation, error behaviour), and the product path
+refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as G
+from test_gpu_models import preset_kwargs
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    from deepvoice3_pytorch_b200 import _build
+    _build.build()
+
+
+def test_library_exports_every_declared_symbol():
+    from deepvoice3_pytorch_b200._lib import parse_header, LIB_PATH
+    decls = parse_header()
+    assert len(decls) >= 20
+    dll = ctypes.CDLL(LIB_PATH)
+    for name in decls:
+        assert hasattr(dll, name), "libdv3b200.so lacks %s declared in include/dv3b200.h" % name
+    assert dll.dv3_abi_version() >= 1
+
+
+@pytest.mark.parametrize("preset", ["deepvoice3_ljspeech", "nyanko_ljspeech", "deepvoice3_vctk"])
+def test_state_dict_and_init_match_reference(preset):
+    """Same keys in the same order, same shapes and -- for the same torch seed -- the same initial values as the
+    reference builder (fingerprints recorded from the live reference by tests/golden/make_golden.py)."""
+    from deepvoice3_pytorch_b200 import builder
+    fp = G.load("init_fingerprints.npz")[preset]
+    bname, kw = preset_kwargs(preset)
+    torch.manual_seed(4321)
+    sd = getattr(builder, bname)(dropout=0.05, **kw).state_dict()
+    assert list(sd.keys()) == [str(k) for k in fp["meta"]["keys"]]
+    assert [str(tuple(v.shape)) for v in sd.values()] == [str(s) for s in fp["meta"]["shapes"]]
+    got = np.array([[float(v.double().sum()), float(v.double().abs().sum()), float(v.flatten()[0])]
+                    for v in sd.values()])
+    np.testing.assert_allclose(got, fp["out"]["fingerprint"], rtol=1e-12, atol=0)
+
+
+def test_builder_error_behaviour():
+    from deepvoice3_pytorch_b200 import builder
+    with pytest.raises(ValueError):
+        builder.nyanko(n_vocab=149, n_speakers=2)                       # reference builder.py:120-121
+    with pytest.raises(ValueError):
+        builder.nyanko(n_vocab=149, downsample_step=1, r=1)             # reference builder.py:122-123
+    with pytest.raises(AssertionError):
+        builder.nyanko(n_vocab=149, encoder_channels=64, decoder_channels=32)
+
+
+def test_trainable_parameters_exclude_position_tables():
+    from deepvoice3_pytorch_b200 import builder
+    m = builder.deepvoice3(n_vocab=149, embed_dim=16, r=1, downsample_step=4, kernel_size=3,
+                           encoder_channels=16, decoder_channels=16, converter_channels=16, linear_dim=33)
+    ids = set(map(id, m.get_trainable_parameters()))
+    dec = m.seq2seq.decoder
+    assert id(dec.embed_query_positions.weight) not in ids and id(dec.embed_keys_positions.weight) not in ids
+    assert id(m.seq2seq.encoder.embed_tokens.weight) in ids
+    m.trainable_positional_encodings = True
+    assert id(dec.embed_query_positions.weight) in set(map(id, m.get_trainable_parameters()))
+
+
+def test_memory_mask_is_bit_exact():
+    from deepvoice3_pytorch_b200.modules import get_mask_from_lengths
+    lengths = np.array([5, 1, 3])
+    mask = get_mask_from_lengths(torch.zeros(3, 5, 2), lengths)
+    want = np.array([[0, 0, 0, 0, 0], [0, 1, 1, 1, 1], [0, 0, 0, 1, 1]], dtype=bool)
+    assert mask.dtype == torch.bool and np.array_equal(mask.numpy(), want)
+
+
+def test_position_table_is_bit_exact():
+    from deepvoice3_pytorch_b200.modules import position_encoding_init, SinusoidalEncoding
+    blocks = G.load("blocks.npz")
+    for j in range(7):
+        case = blocks["sin%d" % j]
+        w = float(case["meta"]["w"])
+        n, d = case["out"]["table"].shape
+        assert np.array_equal(position_encoding_init(n, d, position_rate=w).numpy(), case["out"]["table"])
+    assert np.array_equal(SinusoidalEncoding(64, 32).weight.detach().numpy(), blocks["sin_batch"]["sd"]["weight"])
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA tensors -- never route through a CPU implementation."""
+    from deepvoice3_pytorch_b200 import ops
+    from deepvoice3_pytorch_b200._lib import Dv3Error
+    x = torch.zeros(1, 4, 8)
+    v = torch.ones(8, 4, 3)
+    g = torch.ones(8, 1, 1)
+    with pytest.raises(Dv3Error):
+        ops.convblock(x, v, g, torch.zeros(8))
+    with pytest.raises(Dv3Error):
+        ops.transpose12(x)
+
+
+def test_product_never_imports_oracle():
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deepvoice3_pytorch_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

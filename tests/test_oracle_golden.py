@@ -142,3 +142,21 @@ def test_full_model(name):
                            ins["text_positions"], ins["frame_positions"],
                            case["meta"]["input_lengths"])
     _check_case(case, outs, sd, ins)
+
+
+def test_audio_oracle_mel_basis_and_frames():
+    """The one corroboration the reference tree offers for the (unpinned) audio path: its mel fixture of
+    LJ001-0001 (212 893 samples) has 835 frames; and the Slaney filterbank equals torchaudio's."""
+    from oracle import audio_oracle as A
+    assert A.num_frames(212893) == 835
+    assert A.num_frames(220500) == 865
+    try:
+        import torchaudio
+    except Exception:
+        pytest.skip("torchaudio not importable")
+    ta = torchaudio.functional.melscale_fbanks(513, 125.0, 7600.0, 80, 22050, norm="slaney",
+                                               mel_scale="slaney").T.numpy()
+    np.testing.assert_allclose(A.mel_basis(), ta, rtol=1e-5, atol=1e-6)
+    lin, mel = A.process_utterance(A.synthetic_clip(1, n=22050))
+    assert lin.shape == (A.num_frames(22050), 513) and mel.shape == (A.num_frames(22050), 80)
+    assert lin.min() >= 0 and lin.max() <= 1
