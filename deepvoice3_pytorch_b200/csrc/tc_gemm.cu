@@ -109,7 +109,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             } else {
                 const int bi = it / p.kb_n, tc_ = it - bi * p.kb_n;
                 ax = tc_ * 64; ay = a_row0; az = b_beg + bi;
-                bx = tc_ * 64 + p.tap_off[wg_j]; by0 = b_row0; by1 = b_row1; bz = b_beg + bi;
+                // the tap shift is baked into the wg_j-th shifted copy of the input (tc_split.cu): a TMA box
+                // cannot start at a K (time) coordinate that is not 16-byte aligned
+                bx = tc_ * 64; by0 = b_row0; by1 = b_row1; bz = wg_j * p.B + b_beg + bi;
             }
             mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
             tma_load_3d(st, &mapA_hi, &full[s], ax, ay, az);
@@ -338,7 +340,8 @@ int dv3_tc_conv_wgrad_nsplit(int B, int C, int T, int k) {
     return (B + bps - 1) / bps;
 }
 
-// weight gradient.  dab_hi/lo: (B, 2C, T) bf16 planes; xd_hi/lo: (B, C, T) bf16 planes (dropped-out input);
+// weight gradient.  dab_hi/lo: (B, 2C, T) bf16 planes; xd_hi/lo: (k, B, C, T) bf16 planes, the j-th being the
+// dropped-out input shifted by tap j's offset (dv3_tc_split_input);
 // dw_partials: [nsplit][2C*C*k] fp32 in v's layout (2C, C, k).
 int dv3_tc_conv_wgrad(const void* dab_hi, const void* dab_lo, const void* xd_hi, const void* xd_lo,
                       float* dw_partials, long long split_stride, int B, int C, int T, int k, int dilation,
@@ -348,8 +351,8 @@ int dv3_tc_conv_wgrad(const void* dab_hi, const void* dab_lo, const void* xd_hi,
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     if (encode_tmap_bf16_3d(&a_hi, dab_hi, T, M2, B, (uint64_t)T * 2, (uint64_t)M2 * T * 2, 64, 128)) return 1;
     if (encode_tmap_bf16_3d(&a_lo, dab_lo, T, M2, B, (uint64_t)T * 2, (uint64_t)M2 * T * 2, 64, 128)) return 1;
-    if (encode_tmap_bf16_3d(&b_hi, xd_hi, T, C, B, (uint64_t)T * 2, (uint64_t)C * T * 2, 64, 128)) return 1;
-    if (encode_tmap_bf16_3d(&b_lo, xd_lo, T, C, B, (uint64_t)T * 2, (uint64_t)C * T * 2, 64, 128)) return 1;
+    if (encode_tmap_bf16_3d(&b_hi, xd_hi, T, C, (uint64_t)k * B, (uint64_t)T * 2, (uint64_t)C * T * 2, 64, 128)) return 1;
+    if (encode_tmap_bf16_3d(&b_lo, xd_lo, T, C, (uint64_t)k * B, (uint64_t)T * 2, (uint64_t)C * T * 2, 64, 128)) return 1;
     TcParams p = {};
     p.T = T; p.C = C; p.M2 = M2; p.Cin = C; p.k = k; p.kb_n = (T + 63) / 64; p.B = B;
     fill_taps_tc(p.tap_off, k, dilation, causal, false);

@@ -5,12 +5,19 @@ arithmetic happens in csrc/*.cu.  Every function requires CUDA fp32 tensors and 
 there is no CPU fallback.
 """
 import ctypes
+import os
 
 import torch
 
 from ._lib import lib, Dv3Error
 
 MODE_GLU, MODE_HIGHWAY = 0, 1
+
+# Arithmetic of the ConvBlock contractions:
+#   "fp32"   exact-fp32 CUDA-core kernels (csrc/conv.cu)
+#   "bf16x3" tcgen05 tensor cores with split-bf16 operands, fp32-equivalent accuracy (csrc/tc_gemm.cu); shapes the
+#            tensor-core kernels do not cover (C % 128 != 0, T % 8 != 0) still run on the fp32 kernels.
+conv_math = os.environ.get("DV3_CONV_MATH", "fp32")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -170,11 +177,89 @@ class _ConvBlockFn(torch.autograd.Function):
         return dx, dv, dg, dbias, dspk, None, None, None, None, None, None, None
 
 
+class _ConvBlockTCFn(torch.autograd.Function):
+    """Same contract as _ConvBlockFn on the tcgen05 path: operands are pre-split into bf16 hi/lo planes."""
+
+    @staticmethod
+    def forward(ctx, x, v, g, bias, spk, k, dilation, causal, mode, residual, p_drop, training):
+        _chk(x, v, g, bias, spk)
+        B, C, T = x.shape
+        dev = x.device
+        bf = torch.bfloat16
+        need_bwd = any(ctx.needs_input_grad)
+        inv = torch.empty(2 * C, device=dev)
+        scale = torch.empty_like(inv)
+        wb = torch.empty(2, k, 2 * C, C, device=dev, dtype=bf)       # [hi|lo][k][2C][C]
+        wf = torch.empty(2, k, C, 2 * C, device=dev, dtype=bf)       # [hi|lo][k][C][2C]
+        lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wb[0]), _p(wb[1]), _p(wf[0]),
+                 _p(wf[1]), 2 * C, C, k, _stream())
+        p, seed_ptr, salt = _drop_args(p_drop, training, dev)
+        x_btc = torch.empty(2, B, T, C, device=dev, dtype=bf)
+        x_bct = torch.empty(2, k, B, C, T, device=dev, dtype=bf) if need_bwd else None   # k shifted copies
+        lib.call("dv3_tc_split_input", _p(x), _p(x_btc[0]), _p(x_btc[1]),
+                 _p(x_bct[0]) if need_bwd else None, _p(x_bct[1]) if need_bwd else None, B, C, T, k, dilation,
+                 int(causal), p, seed_ptr, salt, _stream())
+        y = torch.empty_like(x)
+        a = torch.empty_like(x) if need_bwd else None
+        s = torch.empty_like(x) if need_bwd else None
+        lib.call("dv3_tc_convblock_fwd", _p(x_btc[0]), _p(x_btc[1]), _p(wb[0]), _p(wb[1]), _p(bias), _p(spk),
+                 _p(x), _p(y), _p(a), _p(s), B, C, T, k, dilation, int(causal), mode, int(residual), _stream())
+        if need_bwd:
+            ctx.save_for_backward(x, v, g, a, s, x_bct, wf, inv)
+            ctx.cfg = (k, dilation, causal, mode, residual, p, salt, spk is not None, dev)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, v, g, a, s, x_bct, wf, inv = ctx.saved_tensors
+        k, dilation, causal, mode, residual, p, salt, has_spk, dev = ctx.cfg
+        seed_ptr = _p(rng.seed_tensor(dev)) if p > 0 else None
+        dy = _c(dy)
+        B, C, T = x.shape
+        bf = torch.bfloat16
+        d_btc = torch.empty(2, B, T, 2 * C, device=dev, dtype=bf)
+        d_bct = torch.empty(2, B, 2 * C, T, device=dev, dtype=bf)
+        dbias = torch.zeros(2 * C, device=dev)
+        lib.call("dv3_tc_gate_bwd_split", _p(dy), _p(a), _p(s), _p(x), _p(d_btc[0]), _p(d_btc[1]), _p(d_bct[0]),
+                 _p(d_bct[1]), _p(dbias), B, C, T, mode, int(residual), _stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if mode == MODE_GLU:
+                addmode, e1, e2, alpha = (1, dy, None, 0.7071067811865476) if residual else (0, None, None, 0.0)
+            else:
+                addmode, e1, e2, alpha = 2, dy, s, 0.0
+            lib.call("dv3_tc_conv_dgrad", _p(d_btc[0]), _p(d_btc[1]), _p(wf[0]), _p(wf[1]), _p(dx), B, C, T, k,
+                     dilation, int(causal), p, seed_ptr, salt, addmode, _p(e1), _p(e2), alpha, _stream())
+        dv = dg = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            nsplit = lib.raw("dv3_tc_conv_wgrad_nsplit")(B, C, T, k)
+            numel = v.numel()
+            partials = torch.empty(nsplit, numel, device=dev)
+            lib.call("dv3_tc_conv_wgrad", _p(d_bct[0]), _p(d_bct[1]), _p(x_bct[0]), _p(x_bct[1]), _p(partials),
+                     numel, B, C, T, k, dilation, int(causal), _stream())
+            dv, dg = _wn_bwd(partials, nsplit, v, g, inv)
+        dspk = None
+        if has_spk and ctx.needs_input_grad[4]:
+            dspk = d_bct[0, :, :C, :].float() + d_bct[1, :, :C, :].float()
+        return dx, dv, dg, dbias, dspk, None, None, None, None, None, None, None
+
+
+def tc_supported(B, C, T, k):
+    return bool(lib.raw("dv3_tc_supported")(B, C, T, k))
+
+
 def convblock(x, v, g, bias, spk=None, k=3, dilation=1, causal=False, mode=MODE_GLU, residual=True,
               p_drop=0.0, training=False):
     """Fused weight-normed dilated conv + gate.  x (B,C,T); v (2C,C,k); g (2C,1,1); bias (2C);
     spk (B,C,T) already softsign'ed (or None)."""
-    return _ConvBlockFn.apply(_c(x), v, g, bias, None if spk is None else _c(spk), int(k), int(dilation),
+    if conv_math == "bf16x3" and x.is_cuda and tc_supported(x.shape[0], x.shape[1], x.shape[2], int(k)):
+        fn = _ConvBlockTCFn
+    elif conv_math in ("fp32", "bf16x3"):
+        fn = _ConvBlockFn
+    else:
+        raise Dv3Error("unknown conv_math %r" % (conv_math,))
+    return fn.apply(_c(x), v, g, bias, None if spk is None else _c(spk), int(k), int(dilation),
                               bool(causal), int(mode), bool(residual), float(p_drop), bool(training))
 
 

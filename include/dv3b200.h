@@ -140,6 +140,39 @@ int dv3_stft_mel(const float* wav, const int* lengths, const float* mel_basis, c
                  const int* mel_len, float* linear, float* mel, int nclips, int max_len, int max_frames,
                  int n_mels, float preemph, float min_level_db, float ref_level_db, void* stream);
 
+/* ================= tensor-core ("bf16x3") ConvBlock path: tcgen05 + TMA, fp32-equivalent accuracy =================
+ * Same reference code as dv3_convblock_fwd / dv3_conv1d_dgrad / dv3_conv1d_wgrad (modules.py:145-164, 200-226 and
+ * their autograd), computed as hi*hi + hi*lo + lo*hi over bf16 planes hi = bf16(x), lo = bf16(x - hi).
+ * Plane pointers are bf16 device buffers.  Supported when dv3_tc_supported(B, C, T, k) returns 1
+ * (C % 128 == 0, T % 8 == 0, k <= 8); callers use the exact-fp32 entry points otherwise. */
+int dv3_tc_supported(int B, int C, int T, int k);
+/* x (B,C,T) fp32 -> conv-input dropout -> planes in (B,T,C) (forward operand) and k time-shifted copies (k,B,C,T),
+ * copy j = input shifted by tap j's offset, zero padded (weight-gradient operand; pass NULL for both bct pointers
+ * to skip). */
+int dv3_tc_split_input(const float* x, void* btc_hi, void* btc_lo, void* bct_hi, void* bct_lo, int B, int C,
+                       int T, int k, int dilation, int causal, float p_drop, const unsigned long long* seed_ptr,
+                       unsigned salt, void* stream);
+/* weight norm + split: v (Cout,Cin,k), g [Cout] -> planes wb [k][Cout][Cin] (forward) and wf [k][Cin][Cout] (dgrad). */
+int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wb_hi, void* wb_lo,
+                          void* wf_hi, void* wf_lo, int Cout, int Cin, int k, void* stream);
+int dv3_tc_convblock_fwd(const void* xd_hi, const void* xd_lo, const void* w_hi, const void* w_lo,
+                         const float* bias, const float* spk, const float* res, float* y, float* save_a,
+                         float* save_s, int B, int C, int T, int k, int dilation, int causal, int mode,
+                         int residual, void* stream);
+/* gate backward writing dAB = [da ; db] as planes in (B,T,2C) (dgrad operand) and (B,2C,T) (wgrad operand). */
+int dv3_tc_gate_bwd_split(const float* dy, const float* a, const float* s, const float* x, void* btc_hi,
+                          void* btc_lo, void* bct_hi, void* bct_lo, float* dbias, int B, int C, int T, int mode,
+                          int residual, void* stream);
+int dv3_tc_conv_dgrad(const void* dab_hi, const void* dab_lo, const void* w_hi, const void* w_lo, float* dx,
+                      int B, int C, int T, int k, int dilation, int causal, float p_drop,
+                      const unsigned long long* seed_ptr, unsigned salt, int addmode, const float* e1,
+                      const float* e2, float alpha, void* stream);
+int dv3_tc_conv_wgrad_nsplit(int B, int C, int T, int k);
+/* xd_hi/lo here are the (k,B,C,T) shifted copies written by dv3_tc_split_input */
+int dv3_tc_conv_wgrad(const void* dab_hi, const void* dab_lo, const void* xd_hi, const void* xd_lo,
+                      float* dw_partials, long long split_stride, int B, int C, int T, int k, int dilation,
+                      int causal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
