@@ -179,22 +179,44 @@ def run_reference_arm(args):
 # GPU arm
 # -------------------------------------------------------------------------------------------------
 def convblock_roofline(dev, pk, pk_kind):
-    """The dominant kernel of the step: the fused ConvBlock forward at the postnet's widest shape
-    (B=16, C=512, T=800, k=3) -- 2 such blocks fwd (+ same-shaped dgrad/wgrad) are ~38 % of all conv FLOPs.
-    Algorithmic bytes per launch: 4*[2*B*C*T + 2C*C*k + 4C]."""
+    """The dominant kernel of the step: the fused ConvBlock forward GEMM at the postnet's widest shape
+    (B=16, C=512, T=800, k=3) -- the 2 such blocks (+ their same-shaped dgrad/wgrad) are ~38 % of all conv FLOPs.
+    Only the ConvBlock kernel itself is timed (operands prepared outside), CUDA events on the launching stream,
+    L2 flushed between launches.  Algorithmic bytes per launch: 4*[2*B*C*T + 2C*C*k + 4C]."""
     from deepvoice3_pytorch_b200 import ops
     Bc, C, T, k, d = 16, 512, 800, 3, 1
     v = torch.randn(2 * C, C, k, device=dev) * (4.0 / (k * C)) ** 0.5
     g = v.pow(2).sum((1, 2), keepdim=True).sqrt()
     bias = torch.zeros(2 * C, device=dev)
     x = torch.randn(Bc, C, T, device=dev)
-    w_f, w_b, inv = ops._wn_conv_fwd(v, g)
-    y = torch.empty_like(x)
+    y, sa, ss = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    math = ops.conv_math
+    if math == "bf16x3":
+        bf = torch.bfloat16
+        inv, scale = torch.empty(2 * C, device=dev), torch.empty(2 * C, device=dev)
+        wb = torch.empty(2, k, 2 * C, C, device=dev, dtype=bf)
+        wf = torch.empty(2, k, C, 2 * C, device=dev, dtype=bf)
+        ops.lib.call("dv3_tc_weightnorm_fwd", ops._p(v), ops._p(g), ops._p(inv), ops._p(scale), ops._p(wb[0]),
+                     ops._p(wb[1]), ops._p(wf[0]), ops._p(wf[1]), 2 * C, C, k, ops._stream())
+        xs = torch.empty(2, Bc, T, C, device=dev, dtype=bf)
+        ops.lib.call("dv3_tc_split_input", ops._p(x), ops._p(xs[0]), ops._p(xs[1]), None, None, Bc, C, T, k, d, 0,
+                     0.0, None, 0, ops._stream())
+        name = "tc_conv_kernel<FWD> via dv3_tc_convblock_fwd"
 
-    def launch():
-        ops.lib.call("dv3_convblock_fwd", ops._p(x), ops._p(w_f), ops._p(bias), None, ops._p(y), None, None,
-                     Bc, C, T, k, d, 0, 0, 1, 0.0, None, 0, ops._stream())
+        def launch():
+            ops.lib.call("dv3_tc_convblock_fwd", ops._p(xs[0]), ops._p(xs[1]), ops._p(wb[0]), ops._p(wb[1]),
+                         ops._p(bias), None, ops._p(x), ops._p(y), ops._p(sa), ops._p(ss), Bc, C, T, k, d, 0, 0, 1,
+                         ops._stream())
+        mma_passes = 3
+    else:
+        w_f, w_b, inv = ops._wn_conv_fwd(v, g)
+        name = "gemm_simt_kernel<ConvPolicy<gated>> via dv3_convblock_fwd"
+
+        def launch():
+            ops.lib.call("dv3_convblock_fwd", ops._p(x), ops._p(w_f), ops._p(bias), None, ops._p(y), ops._p(sa),
+                         ops._p(ss), Bc, C, T, k, d, 0, 0, 1, 0.0, None, 0, ops._stream())
+        mma_passes = 0
     for _ in range(3):
         launch()
     ts = []
@@ -207,15 +229,21 @@ def convblock_roofline(dev, pk, pk_kind):
     t = float(np.mean(ts))
     alg_bytes = 4.0 * (2 * Bc * C * T + 2 * C * C * k + 4 * C)
     flops = 2.0 * Bc * T * 2 * C * C * k
-    return {
-        "bound": "hbm", "kernel": "dv3_convblock_fwd (B=16,C=512,T=800,k=3)", "achieved": alg_bytes / t / 1e9,
+    r = {
+        "bound": "hbm", "kernel": "%s (B=16,C=512,T=800,k=3)" % name, "achieved": alg_bytes / t / 1e9,
         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / t / 1e9 / pk["hbm_gbs"], "traffic": None,
-        "peak_source": pk_kind, "launch_us": t * 1e6, "alg_bytes": alg_bytes,
-        # the block is a dense contraction (686 FLOP/B): the binding roof is arithmetic, reported beside it
-        "tflops": flops / t / 1e12, "tensor_peak_tflops_bf16": pk["bf16_tflops"],
-        "tensor_frac_of_bf16_peak": flops / t / 1e12 / pk["bf16_tflops"],
-        "math": os.environ.get("DV3_CONV_MATH", "fp32"),
+        "peak_source": pk_kind, "launch_us": t * 1e6, "alg_bytes": alg_bytes, "math": math,
+        # the block is a dense contraction (686 FLOP/B): the binding roof is arithmetic, reported beside the HBM one
+        "fp32_equiv_tflops": flops / t / 1e12,
     }
+    if mma_passes:
+        r["tensor"] = {"bound": "tensor", "achieved": mma_passes * flops / t / 1e12, "peak": pk["bf16_tflops"],
+                       "unit": "TFLOP/s", "frac": mma_passes * flops / t / 1e12 / pk["bf16_tflops"],
+                       "note": "bf16 MMA work actually issued = 3 passes (hi*hi, hi*lo, lo*hi) of the fp32-equivalent flops"}
+    else:
+        r["fp32_fma"] = {"achieved": flops / t / 1e12, "peak": 74.5, "unit": "TFLOP/s", "frac": flops / t / 1e12 / 74.5,
+                         "note": "nominal fp32 FMA peak 148 SM x 128 lanes x 2 x 1.965 GHz"}
+    return r
 
 
 def run_gpu_arm(args):
@@ -294,7 +322,7 @@ def run_gpu_arm(args):
                                "(T_dec=200), random-init weights" % args.preset,
                    "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "inputs larger than L2 (>1.5 GB touched per step)",
-                   "cuda_graph": not args.no_graph, "conv_math": os.environ.get("DV3_CONV_MATH", "fp32")},
+                   "cuda_graph": not args.no_graph, "conv_math": ops.conv_math},
         "e2e": {"value": frames * args.steps / t_e2e, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / args.steps * 1e3},
         "gpu_launches": int(launches), "loss": loss_val, "clocks": clocks.summary(),

@@ -101,7 +101,7 @@ class ParameterArena:
 
     def __init__(self, model, params=None):
         params = list(model.get_trainable_parameters()) if params is None else list(params)
-        assert all(p.is_cuda and p.dtype == torch.float32 for p in params), "model must be on the GPU"
+        assert all(p.dtype == torch.float32 for p in params), "fp32 parameters only"
         self.params = params
         offs, n = [], 0
         for p in params:
@@ -119,6 +119,12 @@ class ParameterArena:
 
     def zero_grad(self):
         self.grad.zero_()
+
+    def all_reduce_grads(self):
+        """The one exchange step of the data-parallel path: sum the flat gradient arena over all ranks (NCCL over
+        NVLink on GPUs; gloo in the CPU tests).  The 1/world average is applied by the optimizer (hyper[3])."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grad)
 
 
 class FlatAdam:
@@ -199,8 +205,7 @@ class TrainStep:
         return loss.detach()
 
     def _exchange_and_update(self):
-        if self.world > 1:
-            dist.all_reduce(self.arena.grad)            # sum; the 1/world average is folded into hyper[3]
+        self.arena.all_reduce_grads()                   # sum; the 1/world average is folded into hyper[3]
         self.opt.apply()
         ops.rng.advance()                               # fresh dropout masks next step (device-side add)
 

@@ -12,7 +12,8 @@ def _check(lin, mel, ref_lin, ref_mel):
     assert lin.shape == ref_lin.shape and mel.shape == ref_mel.shape
     for got, ref in ((lin, ref_lin), (mel, ref_mel)):
         live = ref > 0.05                      # >= 15 dB above the floor
-        assert np.abs(got - ref)[live].max() < 2e-3
+        if live.any():
+            assert np.abs(got - ref)[live].max() < 2e-3
         assert np.abs(got - ref).max() < 2e-2
         assert np.abs(got - ref).mean() < 2e-4
 

@@ -96,9 +96,15 @@ def test_conv_ramp_known_answer():
     (2, 512, 800, 3, 1, False, True, "glu"),
     (16, 256, 200, 3, 9, True, True, "hw"),
 ])
-def test_convblock_canonical_vs_oracle(B, C, T, k, d, causal, residual, mode):
+@pytest.mark.parametrize("math", ["fp32", "bf16x3"])
+def test_convblock_canonical_vs_oracle(B, C, T, k, d, causal, residual, mode, math, monkeypatch):
+    """Both arithmetic modes of the ConvBlock -- exact-fp32 CUDA cores and the tcgen05 split-bf16 path --
+    must meet the same parity bar against the CPU oracle."""
     from deepvoice3_pytorch_b200 import ops
     from oracle import dv3_oracle as O
+    monkeypatch.setattr(ops, "conv_math", math)
+    if math == "bf16x3":
+        assert ops.tc_supported(B, C, T, k), "canonical shapes must run on the tensor-core path"
     gen = torch.Generator().manual_seed(B * 1000 + C + T + d)
     v = torch.randn(2 * C, C, k, generator=gen) * (4.0 / (k * C)) ** 0.5
     g = v.pow(2).sum((1, 2), keepdim=True).sqrt() * (1 + 0.2 * torch.randn(2 * C, 1, 1, generator=gen))
@@ -125,10 +131,12 @@ def test_convblock_canonical_vs_oracle(B, C, T, k, d, causal, residual, mode):
     grad_close(bc.grad, sd["m.conv.bias"].grad.numpy(), "dbias")
 
 
-def test_convblock_dropout_statistics_and_consistency():
+@pytest.mark.parametrize("math,C", [("fp32", 64), ("bf16x3", 128)])
+def test_convblock_dropout_statistics_and_consistency(math, C, monkeypatch):
     """In-kernel dropout: keep-rate ~ 1-p, scale 1/(1-p), and the backward regenerates the same mask."""
     from deepvoice3_pytorch_b200 import ops
-    B, C, T, k = 4, 64, 256, 1
+    monkeypatch.setattr(ops, "conv_math", math)
+    B, T, k = 4, 256, 1
     p = 0.25
     # identity-like block: v = [I ; 0] so a = dropout(x), b = 0 -> s = 0.5 -> y = 0.5*dropout(x)
     v = torch.zeros(2 * C, C, k, device="cuda")
@@ -145,10 +153,10 @@ def test_convblock_dropout_statistics_and_consistency():
     kept = ratio > 0
     rate = kept.float().mean().item()
     assert abs(rate - (1 - p)) < 0.01, rate
-    close(ratio[kept], torch.full_like(ratio[kept], 1 / (1 - p)), rtol=1e-4, atol=1e-5)
+    close(ratio[kept], torch.full_like(ratio[kept], 1 / (1 - p)), rtol=2e-4, atol=1e-5)
     y.sum().backward()
     # dx = 0.5 * mask/(1-p)
-    close(x.grad, 0.5 * kept.float() / (1 - p), rtol=1e-4, atol=1e-5)
+    close(x.grad, 0.5 * kept.float() / (1 - p), rtol=2e-4, atol=1e-5)
     # different salt / seed -> different mask
     ops.rng.start_forward()
     ops.rng.advance()
@@ -156,4 +164,4 @@ def test_convblock_dropout_statistics_and_consistency():
     assert ((y2 > 0) != (y > 0)).float().mean().item() > 0.2
     # eval: no dropout
     y3 = ops.convblock(x, v, g, bias, None, k, 1, False, ops.MODE_GLU, False, p_drop=p, training=False)
-    close(y3, 0.5 * x, rtol=1e-5, atol=1e-6)
+    close(y3, 0.5 * x, rtol=2e-4, atol=1e-6)

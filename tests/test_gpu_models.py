@@ -84,10 +84,13 @@ def synthetic_batch(B, T_text, T_dec, n_speakers, seed, ragged=True):
     return text, mel, tpos, fpos, lengths, spk
 
 
-@pytest.mark.parametrize("preset,B", [("deepvoice3_ljspeech", 4), ("nyanko_ljspeech", 2), ("deepvoice3_vctk", 3)])
-def test_preset_model_vs_oracle(preset, B):
-    """Full-width preset model, T_text=128, T_mel=800 (T_dec=200): forward + every parameter gradient."""
-    from deepvoice3_pytorch_b200 import builder
+@pytest.mark.parametrize("preset,B,math", [("deepvoice3_ljspeech", 4, "fp32"), ("deepvoice3_ljspeech", 4, "bf16x3"),
+                                           ("nyanko_ljspeech", 2, "bf16x3"), ("deepvoice3_vctk", 3, "bf16x3")])
+def test_preset_model_vs_oracle(preset, B, math, monkeypatch):
+    """Full-width preset model, T_text=128, T_mel=800 (T_dec=200): forward + every parameter gradient, in both
+    ConvBlock arithmetic modes (exact-fp32 CUDA cores / tcgen05 split-bf16)."""
+    from deepvoice3_pytorch_b200 import builder, ops
+    monkeypatch.setattr(ops, "conv_math", math)
     from oracle import dv3_oracle as O
     from oracle.specs import spec_from_builder
     bname, kw = preset_kwargs(preset)

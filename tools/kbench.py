@@ -31,6 +31,8 @@ def timeit(fn, iters=20, warmup=3, flush=None):
 
 def main():
     dev = "cuda"
+    if len(sys.argv) > 1:
+        ops.conv_math = sys.argv[1]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     shapes = [(2, 64, 128, 3, 1, False), (16, 256, 200, 3, 9, True), (16, 512, 128, 3, 9, False),
               (16, 256, 800, 3, 3, False), (16, 512, 800, 3, 1, False)]
@@ -53,7 +55,7 @@ def main():
         tfb = timeit(fwdbwd, flush=flush)
         flops = 2.0 * B * T * 2 * C * C * k
         bytes_fwd = 4.0 * (2 * B * C * T + 2 * C * C * k + 4 * C)
-        print(json.dumps(dict(shape=[B, C, T, k, d], fwd_us=tf * 1e6, fwdbwd_us=tfb * 1e6,
+        print(json.dumps(dict(math=ops.conv_math, shape=[B, C, T, k, d], fwd_us=tf * 1e6, fwdbwd_us=tfb * 1e6,
                               fwd_tflops=flops / tf / 1e12, fwdbwd_tflops=3 * flops / tfb / 1e12,
                               fwd_alg_GBps=bytes_fwd / tf / 1e9)))
 
