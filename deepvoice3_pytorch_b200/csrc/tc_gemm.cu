@@ -1,17 +1,22 @@
-// tcgen05 tensor-core path of the ConvBlock: forward, data-gradient and weight-gradient as implicit GEMMs with
-// fp32-equivalent accuracy ("bf16x3"): every fp32 operand is pre-split into bf16 hi + lo planes (by the
-// elementwise kernels in tc_split.cu, which also apply the input dropout and emit the K-major layout each GEMM
-// wants), and each K-step issues hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator (relative error ~2^-16 per
-// product, 50x inside the rtol=1e-3 parity bar; plain TF32 would not be).
+// tcgen05 tensor-core path of the ConvBlock and of the plain (1x1 / k-tap) weight-normed convolutions: forward,
+// data-gradient and weight-gradient as implicit GEMMs with fp32-equivalent accuracy from split-bf16 operands.
+// Every fp32 operand is pre-split into bf16 planes p0 = bf16(x), p1 = bf16(x - p0), [p2 = bf16(x - p0 - p1)]
+// (tc_split.cu, which also applies the input dropout and emits the K-major layout each GEMM wants) and each K-step
+// issues the significant cross products into one fp32 TMEM accumulator:
+//     NPL = 2 ("x3"): p0*p0 + p0*p1 + p1*p0                      ~2^-17 per operand, 1e-5 per block
+//     NPL = 3 ("x6"): + p1*p1 + p0*p2 + p2*p0                    ~2^-24, indistinguishable from fp32 FMA
+// (single-pass TF32 would miss the rtol=1e-3/atol=1e-4 parity bar after ~30 blocks.)
 //
-//   forward : D[t, (a|b) c]  = sum_{j,ci}  Xd[b, t+off_j, ci] * W[j, (a|b) c, ci]     M = 128 time steps, N = 2 x 128
-//   dgrad   : D[t, ci]       = sum_{j,co}  dAB[b, t-off_j, co] * W[j, ci, co]          M = 128 time steps, N = NBOX x 128
-//   wgrad   : D[co, ci] (j)  = sum_{b,t}   dAB[b, co, t] * Xd[b, ci, t+off_j]          M = 128 rows,       N = NBOX x 128
+//   GATED : D[t, (a|b) c] = sum_{j,ci} Xd[b, t+off_j, ci] * W[j, (a|b) c, ci]    M = 128 time steps, N = 128 a | 128 b
+//   CONV  : D[t, n]       = sum_{j,kc} A[b, t+off_j, kc]  * W[j, n, kc]           M = 128 time steps, N = NBOX x 128
+//           (plain conv forward with bias/ReLU, and every data gradient: A = dY or dAB, W = transposed weight)
+//   WGRAD : D[m, n] (j)   = sum_{b,t}  dY[b, m, t] * Xs_j[b, n, t]                 M = 128 rows,       N = NBOX x 128
 //
-// All operands are K-major bf16 tiles of 128 rows x 64 (128 bytes, SWIZZLE_128B) fetched by TMA; the conv's zero
-// padding, the causal shift and ragged tails are TMA out-of-bounds zero fill (negative / >= T coordinates).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer, warps 2-5 =
-// epilogue (TMEM -> registers -> fused gate / mask / residual math -> coalesced global stores along T).
+// All operands are K-major bf16 tiles of 128 rows x BK (BK = 32: 64-byte rows, SWIZZLE_64B; BK = 64: 128-byte rows,
+// SWIZZLE_128B) fetched by TMA; the conv's zero padding, the causal shift, ragged T / channel tails are TMA
+// out-of-bounds zero fill.  Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA
+// issuer, warps 2-5 = epilogue (TMEM -> registers -> fused gate / bias / mask / residual math -> stores coalesced
+// along T).
 #include "tc_common.cuh"
 
 namespace dv3 {
@@ -19,37 +24,65 @@ namespace dv3 {
 using namespace tc;
 
 constexpr int TC_THREADS = 192;
-constexpr int TILE_BYTES = 128 * 128;        // 128 rows x 64 bf16
 constexpr int MAX_TAPS_TC = 8;
+constexpr int SMEM_LIMIT = 232448;          // 227 KB opt-in dynamic shared memory per CTA
 
-enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
+enum { TC_GATED = 0, TC_CONV = 1, TC_WGRAD = 2 };
+
+struct TcMaps { CUtensorMap a[3]; CUtensorMap b[3]; };
 
 struct TcParams {
-    int T, C, M2;              // time steps, block channels, 2*C
-    int k, kb_n;               // taps, 64-wide K blocks per tap (fwd: C/64, dgrad: 2C/64); wgrad: t-chunks per batch
+    int T, B;
+    int Kc;                    // contraction channels per tap (GATED: C, CONV: A channels); WGRAD: unused
+    int Nc;                    // output channels (GATED: C per half, CONV: out channels, WGRAD: N = Cin)
+    int Mw;                    // WGRAD: rows of dY
+    int rows_per_tap;          // rows of the weight matrix per tap (GATED: 2C, CONV: Nc)
+    int k, kb_n;               // taps; K blocks per tap (GATED/CONV) or time chunks per batch (WGRAD)
     int tap_off[MAX_TAPS_TC];
-    // forward epilogue
+    // gated epilogue
     const float* bias; const float* spk; const float* res;
     float* y; float* save_a; float* save_s;
     int gate_mode, residual;
-    // dgrad epilogue
-    float* dx; const float* e1; const float* e2; float alpha; int addmode;
+    // conv epilogue: out = acc*dropmask + bias + addend ; relu
+    float* out; const float* e1; const float* e2; float alpha; int addmode, relu;
     float p_drop; const unsigned long long* seed_ptr; uint32_t salt;
     // wgrad
-    float* dw; long long split_stride; int nsplit, B, batches_per_split, Cin;
+    float* dw; long long split_stride; int nsplit, batches_per_split;
+    int msplit; long long s_m, s_mh, s_n, s_j;
 };
 
-template <int MODE, int NBOX>
+template <int BK> struct SwizzleOf;
+template <> struct SwizzleOf<64> { static constexpr uint32_t layout = 2, sbo = 1024; };   // SWIZZLE_128B
+template <> struct SwizzleOf<32> { static constexpr uint32_t layout = 4, sbo = 512; };    // SWIZZLE_64B
+
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                 // start address / 16
+    d |= (uint64_t)(SwizzleOf<BK>::sbo >> 4) << 32;          // stride between 8-row swizzle atoms
+    d |= (uint64_t)1 << 46;                                  // sm_100 descriptor version
+    d |= (uint64_t)SwizzleOf<BK>::layout << 61;
+    return d;
+}
+
+template <int NBOX, int BK, int NPL>
+struct TcCfg {
+    static constexpr int TILE = 128 * BK * 2;
+    static constexpr int STAGE = NPL * (1 + NBOX) * TILE;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int SMEM = STAGES * STAGE + 1024 + 512;
+    static constexpr int NCOLS = 128 * NBOX;
+};
+
+template <int MODE, int NBOX, int BK, int NPL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
-               const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
-               const __grid_constant__ TcParams p) {
-    constexpr int STAGE_BYTES = (2 + 2 * NBOX) * TILE_BYTES;
-    constexpr int STAGES = NBOX == 2 ? 2 : 3;
-    constexpr int NCOLS = 128 * NBOX;
+tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+    using Cfg = TcCfg<NBOX, BK, NPL>;
+    constexpr int TILE = Cfg::TILE, STAGE = Cfg::STAGE, STAGES = Cfg::STAGES, NCOLS = Cfg::NCOLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -57,33 +90,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- tile coordinates ----------------------------------------------------------------------
-    int a_row0, a_z, b_row0, b_row1, n_iters, it_base = 0, wg_j = 0, wg_split = 0, b_beg = 0;
-    if (MODE == TC_FWD) {
-        a_row0 = blockIdx.x * 128;                       // t0
-        a_z = blockIdx.z;                                // batch
-        b_row0 = blockIdx.y * 128;                       // c0 (a half); b half at + C
-        b_row1 = p.C + blockIdx.y * 128;
+    int a_row0, a_z = 0, b_row0, b_row1, n_iters, wg_j = 0, wg_split = 0, b_beg = 0;
+    if (MODE == TC_GATED) {
+        a_row0 = blockIdx.x * 128; a_z = blockIdx.z;                 // t0, batch
+        b_row0 = blockIdx.y * 128; b_row1 = p.Nc + blockIdx.y * 128; // a half, b half
         n_iters = p.k * p.kb_n;
-    } else if (MODE == TC_DGRAD) {
-        a_row0 = blockIdx.x * 128;
-        a_z = blockIdx.z;
-        b_row0 = blockIdx.y * 128 * NBOX;                // ci0
-        b_row1 = b_row0 + 128;
+    } else if (MODE == TC_CONV) {
+        a_row0 = blockIdx.x * 128; a_z = blockIdx.z;
+        b_row0 = blockIdx.y * 128 * NBOX; b_row1 = b_row0 + 128;     // n0
         n_iters = p.k * p.kb_n;
     } else {
         wg_j = blockIdx.z % p.k; wg_split = blockIdx.z / p.k;
-        a_row0 = blockIdx.y * 128;                       // co0
-        b_row0 = blockIdx.x * 128 * NBOX;                // ci0
-        b_row1 = b_row0 + 128;
+        a_row0 = blockIdx.y * 128;                                   // m0
+        b_row0 = blockIdx.x * 128 * NBOX; b_row1 = b_row0 + 128;     // n0
         b_beg = wg_split * p.batches_per_split;
         int b_end = b_beg + p.batches_per_split; if (b_end > p.B) b_end = p.B;
         n_iters = (b_end > b_beg ? b_end - b_beg : 0) * p.kb_n;
-        a_z = 0;
     }
-    (void)it_base;
 
     if (threadIdx.x == 0) {
-        prefetch_tmap(&mapA_hi); prefetch_tmap(&mapA_lo); prefetch_tmap(&mapB_hi); prefetch_tmap(&mapB_lo);
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) { prefetch_tmap(&maps.a[i]); prefetch_tmap(&maps.b[i]); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
@@ -99,27 +126,26 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         for (int it = 0; it < n_iters; ++it) {
             const int s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* st = smem + s * STAGE_BYTES;
+            uint8_t* st = smem + s * STAGE;
             int ax, ay, az, bx, by0, by1, bz;
-            if (MODE == TC_FWD || MODE == TC_DGRAD) {
-                const int j = it / p.kb_n, kb = it - j * p.kb_n;
-                ax = kb * 64; ay = a_row0 + p.tap_off[j]; az = a_z;
-                const int rows_per_tap = (MODE == TC_FWD) ? p.M2 : p.C;
-                bx = kb * 64; by0 = j * rows_per_tap + b_row0; by1 = j * rows_per_tap + b_row1; bz = 0;
-            } else {
+            if (MODE == TC_WGRAD) {
                 const int bi = it / p.kb_n, tc_ = it - bi * p.kb_n;
-                ax = tc_ * 64; ay = a_row0; az = b_beg + bi;
+                ax = tc_ * BK; ay = a_row0; az = b_beg + bi;
                 // the tap shift is baked into the wg_j-th shifted copy of the input (tc_split.cu): a TMA box
                 // cannot start at a K (time) coordinate that is not 16-byte aligned
-                bx = tc_ * 64; by0 = b_row0; by1 = b_row1; bz = wg_j * p.B + b_beg + bi;
+                bx = tc_ * BK; by0 = b_row0; by1 = b_row1; bz = wg_j * p.B + b_beg + bi;
+            } else {
+                const int j = it / p.kb_n, kb = it - j * p.kb_n;
+                ax = kb * BK; ay = a_row0 + p.tap_off[j]; az = a_z;
+                bx = kb * BK; by0 = j * p.rows_per_tap + b_row0; by1 = j * p.rows_per_tap + b_row1; bz = 0;
             }
-            mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-            tma_load_3d(st, &mapA_hi, &full[s], ax, ay, az);
-            tma_load_3d(st + TILE_BYTES, &mapA_lo, &full[s], ax, ay, az);
-            tma_load_3d(st + 2 * TILE_BYTES, &mapB_hi, &full[s], bx, by0, bz);
-            if (NBOX == 2) tma_load_3d(st + 3 * TILE_BYTES, &mapB_hi, &full[s], bx, by1, bz);
-            tma_load_3d(st + (2 + NBOX) * TILE_BYTES, &mapB_lo, &full[s], bx, by0, bz);
-            if (NBOX == 2) tma_load_3d(st + (3 + NBOX) * TILE_BYTES, &mapB_lo, &full[s], bx, by1, bz);
+            mbar_arrive_expect_tx(&full[s], STAGE);
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) {
+                tma_load_3d(st + pl * TILE, &maps.a[pl], &full[s], ax, ay, az);
+                tma_load_3d(st + (NPL + pl * NBOX) * TILE, &maps.b[pl], &full[s], bx, by0, bz);
+                if (NBOX == 2) tma_load_3d(st + (NPL + pl * NBOX + 1) * TILE, &maps.b[pl], &full[s], bx, by1, bz);
+            }
         }
     } else if (warp == 1 && lane == 0) {
         // ================= MMA issuer =================
@@ -128,32 +154,37 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             const int s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(&full[s], ph);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-            const uint64_t a_hi = make_smem_desc_sw128(sa), a_lo = make_smem_desc_sw128(sa + TILE_BYTES);
-            const uint64_t b_hi = make_smem_desc_sw128(sa + 2 * TILE_BYTES);
-            const uint64_t b_lo = make_smem_desc_sw128(sa + (2 + NBOX) * TILE_BYTES);
+            const uint32_t sa = smem_u32(smem + s * STAGE);
+            uint64_t da[NPL], db[NPL];
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {               // 4 x UMMA_K(16) = 64
-                const uint64_t adv = (uint64_t)(kk * 2);   // 32 bytes >> 4
-                umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, (it | kk) != 0);
-                umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
-                umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
+            for (int pl = 0; pl < NPL; ++pl) {
+                da[pl] = make_desc<BK>(sa + pl * TILE);
+                db[pl] = make_desc<BK>(sa + (NPL + pl * NBOX) * TILE);
             }
-            umma_commit(&empty[s]);                        // frees the stage once these MMAs retire
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+                const uint64_t adv = (uint64_t)(kk * 2);             // 16 bf16 = 32 bytes, in 16-byte units
+                umma_bf16(tmem_base, da[0] + adv, db[0] + adv, idesc, (it | kk) != 0);
+                umma_bf16(tmem_base, da[0] + adv, db[1] + adv, idesc, 1);
+                umma_bf16(tmem_base, da[1] + adv, db[0] + adv, idesc, 1);
+                if (NPL == 3) {
+                    umma_bf16(tmem_base, da[1] + adv, db[1] + adv, idesc, 1);
+                    umma_bf16(tmem_base, da[0] + adv, db[2] + adv, idesc, 1);
+                    umma_bf16(tmem_base, da[2] + adv, db[0] + adv, idesc, 1);
+                }
+            }
+            umma_commit(&empty[s]);                                  // frees the stage once these MMAs retire
         }
         umma_commit(tmem_full);
     } else if (warp >= 2) {
         // ================= epilogue =================
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        const int q = warp & 3;                            // TMEM lane quarter this warp may touch
-        const int row = q * 32 + lane;                     // accumulator row (M index)
+        const int q = warp & 3;                                      // TMEM lane quarter this warp may touch
+        const int row = q * 32 + lane;                               // accumulator row (M index)
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (n_iters == 0) {
-            // nothing accumulated (only possible for an empty wgrad split): treat as zeros
-        }
-        if (MODE == TC_FWD) {
-            const int t = a_row0 + row, b = a_z;
+        if (MODE == TC_GATED) {
+            const int t = a_row0 + row, b = a_z, C = p.Nc;
             const bool tv = t < p.T;
             for (int c32 = 0; c32 < 128; c32 += 32) {
                 float va[32], vb[32];
@@ -163,10 +194,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const int c = b_row0 + c32 + i;
-                    const size_t idx = ((size_t)b * p.C + c) * p.T + t;
+                    const size_t idx = ((size_t)b * C + c) * p.T + t;
                     float a = va[i] + p.bias[c];
                     if (p.spk) a += p.spk[idx];
-                    const float s = sigmoidf_(vb[i] + p.bias[p.C + c]);
+                    const float s = sigmoidf_(vb[i] + p.bias[C + c]);
                     float y;
                     if (p.gate_mode == 0) {
                         y = a * s;
@@ -179,7 +210,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                     if (p.save_s) p.save_s[idx] = s;
                 }
             }
-        } else if (MODE == TC_DGRAD) {
+        } else if (MODE == TC_CONV) {
             const int t = a_row0 + row, b = a_z;
             const bool tv = t < p.T;
             const DropCfg drop = make_drop(p.p_drop, p.seed_ptr, p.salt);
@@ -189,26 +220,29 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 if (!tv) continue;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const int ci = b_row0 + c32 + i;
-                    if (ci >= p.C) continue;
-                    const size_t idx = ((size_t)b * p.C + ci) * p.T + t;
+                    const int n = b_row0 + c32 + i;
+                    if (n >= p.Nc) continue;
+                    const size_t idx = ((size_t)b * p.Nc + n) * p.T + t;
                     float g = v[i] * drop_scale(drop, (uint32_t)idx);
+                    if (p.bias) g += p.bias[n];
                     if (p.addmode == 1) g += p.alpha * p.e1[idx];
                     else if (p.addmode == 2) g += p.e1[idx] * (1.f - p.e2[idx]);
-                    p.dx[idx] = g;
+                    if (p.relu) g = fmaxf(g, 0.f);
+                    p.out[idx] = g;
                 }
             }
         } else {
-            const int co = a_row0 + row;
-            float* out = p.dw + (size_t)wg_split * p.split_stride + wg_j;
+            const int m = a_row0 + row;
+            float* out = p.dw + (size_t)wg_split * p.split_stride + (size_t)wg_j * p.s_j;
+            const size_t ma = (size_t)(m % p.msplit) * p.s_m + (size_t)(m / p.msplit) * p.s_mh;
             for (int c32 = 0; c32 < NCOLS; c32 += 32) {
                 float v[32];
                 tmem_ld_32x32(taddr + c32, v);
-                if (co >= p.M2) continue;
+                if (m >= p.Mw) continue;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const int ci = b_row0 + c32 + i;
-                    if (ci < p.Cin) out[((size_t)co * p.Cin + ci) * p.k] = (n_iters > 0) ? v[i] : 0.f;
+                    const int n = b_row0 + c32 + i;
+                    if (n < p.Nc) out[ma + (size_t)n * p.s_n] = (n_iters > 0) ? v[i] : 0.f;
                 }
             }
         }
@@ -226,6 +260,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
+// bf16 3-D tensor map; box = (bk, 128, 1); swizzle chosen from the box width (64 or 128 bytes)
 int encode_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                         uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
     if (!g_encode) {
@@ -242,9 +277,10 @@ int encode_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_
     cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
     cuuint32_t box[3] = {box0, box1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle sw = box0 * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
-                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u)", (int)r,
                   (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
@@ -254,85 +290,133 @@ int encode_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_
     return 0;
 }
 
-template <int MODE, int NBOX>
-static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                     const CUtensorMap& b_lo, const TcParams& p, dim3 grid, cudaStream_t st, const char* what) {
-    constexpr int STAGES = NBOX == 2 ? 2 : 3;
-    constexpr int SMEM = STAGES * (2 + 2 * NBOX) * TILE_BYTES + 1024 + 256;
+template <int MODE, int NBOX, int BK, int NPL>
+static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStream_t st, const char* what) {
+    using Cfg = TcCfg<NBOX, BK, NPL>;
+    static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<MODE, NBOX>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        if (e != cudaSuccess) { set_error("%s: cannot set %d B dynamic smem: %s", what, SMEM, cudaGetErrorString(e)); return 1; }
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<MODE, NBOX, BK, NPL>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) {
+            set_error("%s: cannot set %d B dynamic smem: %s", what, Cfg::SMEM, cudaGetErrorString(e));
+            return 1;
+        }
         configured = true;
     }
-    tc_conv_kernel<MODE, NBOX><<<grid, TC_THREADS, SMEM, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    tc_conv_kernel<MODE, NBOX, BK, NPL><<<grid, TC_THREADS, Cfg::SMEM, st>>>(maps, p);
     return check_launch(what);
+}
+
+static int g_bk = 0;
+static int tc_bk() {                       // K-block width: 32 (SWIZZLE_64B, deeper pipeline) unless DV3_TC_BK=64
+    if (!g_bk) {
+        const char* e = getenv("DV3_TC_BK");
+        g_bk = (e && atoi(e) == 64) ? 64 : 32;
+    }
+    return g_bk;
 }
 
 static void fill_taps_tc(int* tap_off, int k, int dilation, int causal, bool transpose) {
     const int padl = causal ? (k - 1) * dilation : (k - 1) / 2 * dilation;
-    for (int j = 0; j < k; ++j) tap_off[j] = transpose ? (padl - j * dilation) : (j * dilation - padl);
+    for (int j = 0; j < MAX_TAPS_TC; ++j)
+        tap_off[j] = j < k ? (transpose ? (padl - j * dilation) : (j * dilation - padl)) : 0;
+}
+
+// plane p of a [nplanes][...] bf16 buffer
+static inline const void* plane(const void* base, int pl, long long plane_elems) {
+    return (const char*)base + (size_t)pl * plane_elems * 2;
 }
 
 }  // namespace dv3
 
 using namespace dv3;
-typedef __nv_bfloat16 bf16;
 
 extern "C" {
 
-// 1 if the tensor-core path supports this block shape (else the caller must use the exact-fp32 kernels)
+int dv3_tc_k_block(void) { return tc_bk(); }
+
+// 1 if the tensor-core ConvBlock path supports this block shape (else the caller uses the exact-fp32 kernels)
 int dv3_tc_supported(int B, int C, int T, int k) {
     return (C % 128 == 0) && (T % 8 == 0) && k >= 1 && k <= MAX_TAPS_TC && B >= 1 && B <= 65535;
 }
+// plain convs: any channel counts (planes are padded to a multiple of 8 channels), T % 8 == 0; k-tap convs need
+// Cout % 128 == 0 so a weight box never straddles two taps
+int dv3_tc_conv_supported(int B, int Cin, int Cout, int T, int k) {
+    return (T % 8 == 0) && k >= 1 && k <= MAX_TAPS_TC && B >= 1 && B <= 65535 && (k == 1 || Cout % 128 == 0) &&
+           Cin >= 8 && Cout >= 1;
+}
 
-// forward.  xd_hi/xd_lo: (B, T, C) bf16 planes of the (dropped-out) input; w_hi/w_lo: [k][2C][C] bf16 planes of
-// the normalised weight; everything else as dv3_convblock_fwd.
-int dv3_tc_convblock_fwd(const void* xd_hi, const void* xd_lo, const void* w_hi, const void* w_lo,
-                         const float* bias, const float* spk, const float* res, float* y, float* save_a,
-                         float* save_s, int B, int C, int T, int k, int dilation, int causal, int mode,
-                         int residual, void* stream) {
+// Gated forward.  xd: [npl][B][T][C] bf16 planes of the (dropped-out) input; w: [npl][k][2C][C] bf16 planes of the
+// normalised weight; npl = 2 ("x3") or 3 ("x6"); the rest as dv3_convblock_fwd.
+int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bias, const float* spk,
+                         const float* res, float* y, float* save_a, float* save_s, int B, int C, int T, int k,
+                         int dilation, int causal, int mode, int residual, void* stream) {
     DV3_REQUIRE(dv3_tc_supported(B, C, T, k), "tc_convblock_fwd: unsupported shape B=%d C=%d T=%d k=%d", B, C, T, k);
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;
-    if (encode_tmap_bf16_3d(&a_hi, xd_hi, C, T, B, (uint64_t)C * 2, (uint64_t)T * C * 2, 64, 128)) return 1;
-    if (encode_tmap_bf16_3d(&a_lo, xd_lo, C, T, B, (uint64_t)C * 2, (uint64_t)T * C * 2, 64, 128)) return 1;
-    if (encode_tmap_bf16_3d(&b_hi, w_hi, C, (uint64_t)k * 2 * C, 1, (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, 64, 128)) return 1;
-    if (encode_tmap_bf16_3d(&b_lo, w_lo, C, (uint64_t)k * 2 * C, 1, (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, 64, 128)) return 1;
+    DV3_REQUIRE(npl == 2 || npl == 3, "tc_convblock_fwd: npl must be 2 or 3");
+    const int bk = npl == 3 ? 32 : tc_bk();
+    TcMaps maps;
+    for (int pl = 0; pl < npl; ++pl) {
+        if (encode_tmap_bf16_3d(&maps.a[pl], plane(xd, pl, (long long)B * T * C), C, T, B, (uint64_t)C * 2,
+                                (uint64_t)T * C * 2, bk, 128)) return 1;
+        if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
+                                (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 128)) return 1;
+    }
     TcParams p = {};
-    p.T = T; p.C = C; p.M2 = 2 * C; p.k = k; p.kb_n = C / 64;
+    p.T = T; p.B = B; p.Kc = C; p.Nc = C; p.rows_per_tap = 2 * C; p.k = k; p.kb_n = (C + bk - 1) / bk;
     fill_taps_tc(p.tap_off, k, dilation, causal, false);
     p.bias = bias; p.spk = spk; p.res = res; p.y = y; p.save_a = save_a; p.save_s = save_s;
     p.gate_mode = mode; p.residual = residual;
     dim3 grid((T + 127) / 128, C / 128, B);
-    return launch_tc<TC_FWD, 2>(a_hi, a_lo, b_hi, b_lo, p, grid, (cudaStream_t)stream, "tc_convblock_fwd");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (npl == 3) return launch_tc<TC_GATED, 2, 32, 3>(maps, p, grid, st, "tc_convblock_fwd(x6)");
+    if (bk == 64) return launch_tc<TC_GATED, 2, 64, 2>(maps, p, grid, st, "tc_convblock_fwd");
+    return launch_tc<TC_GATED, 2, 32, 2>(maps, p, grid, st, "tc_convblock_fwd");
 }
 
-// data gradient.  dab_hi/lo: (B, T, 2C) bf16 planes; w_hi/lo: [k][C][2C] bf16 planes; dx (B, C, T) fp32.
-int dv3_tc_conv_dgrad(const void* dab_hi, const void* dab_lo, const void* w_hi, const void* w_lo, float* dx,
-                      int B, int C, int T, int k, int dilation, int causal, float p_drop,
-                      const unsigned long long* seed_ptr, unsigned salt, int addmode, const float* e1,
-                      const float* e2, float alpha, void* stream) {
-    DV3_REQUIRE(dv3_tc_supported(B, C, T, k), "tc_conv_dgrad: unsupported shape B=%d C=%d T=%d k=%d", B, C, T, k);
-    const int M2 = 2 * C;
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;
-    if (encode_tmap_bf16_3d(&a_hi, dab_hi, M2, T, B, (uint64_t)M2 * 2, (uint64_t)T * M2 * 2, 64, 128)) return 1;
-    if (encode_tmap_bf16_3d(&a_lo, dab_lo, M2, T, B, (uint64_t)M2 * 2, (uint64_t)T * M2 * 2, 64, 128)) return 1;
-    if (encode_tmap_bf16_3d(&b_hi, w_hi, M2, (uint64_t)k * C, 1, (uint64_t)M2 * 2, (uint64_t)k * C * M2 * 2, 64, 128)) return 1;
-    if (encode_tmap_bf16_3d(&b_lo, w_lo, M2, (uint64_t)k * C, 1, (uint64_t)M2 * 2, (uint64_t)k * C * M2 * 2, 64, 128)) return 1;
+// Generic conv / data-gradient:  out (B, Nc, T) fp32 = sum_j A[b, t+off_j, :] . W[j, n, :]  (+ epilogue)
+//   a: [npl][B][T][Kp] bf16 planes, Kp = Kc rounded up to 8;  w: [npl][k][Nc][Kp] bf16 planes; npl = 2 | 3.
+//   transpose_taps = 1 for a data gradient (offsets padl - j*d), 0 for a forward conv.
+int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc, int Nc, int T, int k, int dilation,
+                int causal, int transpose_taps, const float* bias, int relu, float p_drop,
+                const unsigned long long* seed_ptr, unsigned salt, int addmode, const float* e1, const float* e2,
+                float alpha, void* stream) {
+    DV3_REQUIRE(T % 8 == 0 && k >= 1 && k <= MAX_TAPS_TC && (k == 1 || Nc % 128 == 0) && B <= 65535,
+                "tc_conv: unsupported shape B=%d Kc=%d Nc=%d T=%d k=%d", B, Kc, Nc, T, k);
+    DV3_REQUIRE(npl == 2 || npl == 3, "tc_conv: npl must be 2 or 3");
+    const int bk = npl == 3 ? 32 : tc_bk();
+    const int Kp = (Kc + 7) / 8 * 8;
+    TcMaps maps;
+    for (int pl = 0; pl < npl; ++pl) {
+        if (encode_tmap_bf16_3d(&maps.a[pl], plane(a, pl, (long long)B * T * Kp), Kc, T, B, (uint64_t)Kp * 2,
+                                (uint64_t)T * Kp * 2, bk, 128)) return 1;
+        if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
+                                (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, 128)) return 1;
+    }
     TcParams p = {};
-    p.T = T; p.C = C; p.M2 = M2; p.k = k; p.kb_n = M2 / 64;
-    fill_taps_tc(p.tap_off, k, dilation, causal, true);
-    p.dx = dx; p.e1 = e1; p.e2 = e2; p.alpha = alpha; p.addmode = addmode;
+    p.T = T; p.B = B; p.Kc = Kc; p.Nc = Nc; p.rows_per_tap = Nc; p.k = k; p.kb_n = (Kc + bk - 1) / bk;
+    fill_taps_tc(p.tap_off, k, dilation, causal, transpose_taps != 0);
+    p.out = out; p.bias = bias; p.relu = relu; p.e1 = e1; p.e2 = e2; p.alpha = alpha; p.addmode = addmode;
     p.p_drop = p_drop; p.seed_ptr = seed_ptr; p.salt = salt;
     cudaStream_t st = (cudaStream_t)stream;
-    if (C % 256 == 0)
-        return launch_tc<TC_DGRAD, 2>(a_hi, a_lo, b_hi, b_lo, p, dim3((T + 127) / 128, C / 256, B), st, "tc_conv_dgrad");
-    return launch_tc<TC_DGRAD, 1>(a_hi, a_lo, b_hi, b_lo, p, dim3((T + 127) / 128, C / 128, B), st, "tc_conv_dgrad");
+    const int t_tiles = (T + 127) / 128;
+    // two 128-column boxes per CTA only when that still fills the machine
+    const bool wide = Nc > 128 && (long long)t_tiles * ((Nc + 255) / 256) * B >= 120;
+    if (wide) {
+        dim3 grid(t_tiles, (Nc + 255) / 256, B);
+        if (npl == 3) return launch_tc<TC_CONV, 2, 32, 3>(maps, p, grid, st, "tc_conv(x6)");
+        if (bk == 64) return launch_tc<TC_CONV, 2, 64, 2>(maps, p, grid, st, "tc_conv");
+        return launch_tc<TC_CONV, 2, 32, 2>(maps, p, grid, st, "tc_conv");
+    }
+    dim3 grid(t_tiles, (Nc + 127) / 128, B);
+    if (npl == 3) return launch_tc<TC_CONV, 1, 32, 3>(maps, p, grid, st, "tc_conv(x6)");
+    if (bk == 64) return launch_tc<TC_CONV, 1, 64, 2>(maps, p, grid, st, "tc_conv");
+    return launch_tc<TC_CONV, 1, 32, 2>(maps, p, grid, st, "tc_conv");
 }
 
-int dv3_tc_conv_wgrad_nsplit(int B, int C, int T, int k) {
-    const int tiles = (2 * C / 128) * ((C % 256 == 0) ? C / 256 : C / 128) * k;
+int dv3_tc_wgrad_nsplit(int B, int Mw, int Nw, int T, int k) {
+    const int nt = Nw > 128 ? (Nw + 255) / 256 : 1;
+    const int tiles = ((Mw + 127) / 128) * nt * k;
     int want = (2 * 148 + tiles - 1) / tiles;
     if (want > B) want = B;
     if (want < 1) want = 1;
@@ -340,29 +424,36 @@ int dv3_tc_conv_wgrad_nsplit(int B, int C, int T, int k) {
     return (B + bps - 1) / bps;
 }
 
-// weight gradient.  dab_hi/lo: (B, 2C, T) bf16 planes; xd_hi/lo: (k, B, C, T) bf16 planes, the j-th being the
-// dropped-out input shifted by tap j's offset (dv3_tc_split_input);
-// dw_partials: [nsplit][2C*C*k] fp32 in v's layout (2C, C, k).
-int dv3_tc_conv_wgrad(const void* dab_hi, const void* dab_lo, const void* xd_hi, const void* xd_lo,
-                      float* dw_partials, long long split_stride, int B, int C, int T, int k, int dilation,
-                      int causal, void* stream) {
-    DV3_REQUIRE(dv3_tc_supported(B, C, T, k), "tc_conv_wgrad: unsupported shape B=%d C=%d T=%d k=%d", B, C, T, k);
-    const int M2 = 2 * C;
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;
-    if (encode_tmap_bf16_3d(&a_hi, dab_hi, T, M2, B, (uint64_t)T * 2, (uint64_t)M2 * T * 2, 64, 128)) return 1;
-    if (encode_tmap_bf16_3d(&a_lo, dab_lo, T, M2, B, (uint64_t)T * 2, (uint64_t)M2 * T * 2, 64, 128)) return 1;
-    if (encode_tmap_bf16_3d(&b_hi, xd_hi, T, C, (uint64_t)k * B, (uint64_t)T * 2, (uint64_t)C * T * 2, 64, 128)) return 1;
-    if (encode_tmap_bf16_3d(&b_lo, xd_lo, T, C, (uint64_t)k * B, (uint64_t)T * 2, (uint64_t)C * T * 2, 64, 128)) return 1;
+// Weight gradient.  dy: [2][B][Mw][T] bf16 planes; xs: [2][k][B][Nw][T] bf16 planes (k time-shifted copies of the
+// conv input, dv3_tc_split_input); partial element (m, n, j) at (m%msplit)*s_m + (m/msplit)*s_mh + n*s_n + j*s_j.
+int dv3_tc_wgrad(const void* dy, const void* xs, float* dw_partials, long long split_stride, int B, int Mw, int Nw,
+                 int T, int k, int msplit, long long s_m, long long s_mh, long long s_n, long long s_j,
+                 void* stream) {
+    DV3_REQUIRE(T % 8 == 0 && k >= 1 && k <= MAX_TAPS_TC && B <= 65535, "tc_wgrad: unsupported shape T=%d k=%d", T, k);
+    const int bk = tc_bk();
+    TcMaps maps;
+    for (int pl = 0; pl < 2; ++pl) {
+        if (encode_tmap_bf16_3d(&maps.a[pl], plane(dy, pl, (long long)B * Mw * T), T, Mw, B, (uint64_t)T * 2,
+                                (uint64_t)Mw * T * 2, bk, 128)) return 1;
+        if (encode_tmap_bf16_3d(&maps.b[pl], plane(xs, pl, (long long)k * B * Nw * T), T, Nw, (uint64_t)k * B,
+                                (uint64_t)T * 2, (uint64_t)Nw * T * 2, bk, 128)) return 1;
+    }
     TcParams p = {};
-    p.T = T; p.C = C; p.M2 = M2; p.Cin = C; p.k = k; p.kb_n = (T + 63) / 64; p.B = B;
-    fill_taps_tc(p.tap_off, k, dilation, causal, false);
-    p.nsplit = dv3_tc_conv_wgrad_nsplit(B, C, T, k);
+    p.T = T; p.B = B; p.Mw = Mw; p.Nc = Nw; p.k = k; p.kb_n = (T + bk - 1) / bk;
+    p.nsplit = dv3_tc_wgrad_nsplit(B, Mw, Nw, T, k);
     p.batches_per_split = (B + p.nsplit - 1) / p.nsplit;
     p.dw = dw_partials; p.split_stride = split_stride;
+    p.msplit = msplit; p.s_m = s_m; p.s_mh = s_mh; p.s_n = s_n; p.s_j = s_j;
     cudaStream_t st = (cudaStream_t)stream;
-    if (C % 256 == 0)
-        return launch_tc<TC_WGRAD, 2>(a_hi, a_lo, b_hi, b_lo, p, dim3(C / 256, M2 / 128, p.nsplit * k), st, "tc_conv_wgrad");
-    return launch_tc<TC_WGRAD, 1>(a_hi, a_lo, b_hi, b_lo, p, dim3(C / 128, M2 / 128, p.nsplit * k), st, "tc_conv_wgrad");
+    const int m_tiles = (Mw + 127) / 128;
+    if (Nw > 128) {
+        dim3 grid((Nw + 255) / 256, m_tiles, p.nsplit * k);
+        if (bk == 64) return launch_tc<TC_WGRAD, 2, 64, 2>(maps, p, grid, st, "tc_wgrad");
+        return launch_tc<TC_WGRAD, 2, 32, 2>(maps, p, grid, st, "tc_wgrad");
+    }
+    dim3 grid(1, m_tiles, p.nsplit * k);
+    if (bk == 64) return launch_tc<TC_WGRAD, 1, 64, 2>(maps, p, grid, st, "tc_wgrad");
+    return launch_tc<TC_WGRAD, 1, 32, 2>(maps, p, grid, st, "tc_wgrad");
 }
 
 }  // extern "C"

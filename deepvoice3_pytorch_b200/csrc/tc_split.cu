@@ -1,7 +1,9 @@
-// Operand preparation for the tensor-core ConvBlock (tc_gemm.cu): every fp32 operand x becomes two bf16 planes
-// hi = bf16(x), lo = bf16(x - hi), written in the K-major layout each implicit GEMM consumes.  These passes are
-// pure HBM streaming (read 4 B, write 4-8 B per element) and absorb work the fp32 path does inside its loaders:
-// the conv-input dropout mask and the (B,C,T) <-> (B,T,C) layout change.
+// Operand preparation for the tensor-core path (tc_gemm.cu): every fp32 operand x becomes bf16 planes
+// p0 = bf16(x), p1 = bf16(x - p0) [, p2 = bf16(x - p0 - p1)], written in the K-major layout each implicit GEMM
+// consumes.  These passes are pure HBM streaming (read 4 B, write 4-12 B per element) and absorb work the fp32 path
+// does inside its loaders: the conv-input dropout mask, the ReLU mask of the incoming gradient, the bias-gradient
+// reduction and the (B,C,T) <-> (B,T,C) layout change.  Channel pitches are padded to a multiple of 8 (16 bytes,
+// the TMA stride granularity); pad columns are never read (the tensor maps carry the true extent).
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -9,25 +11,34 @@ namespace dv3 {
 
 typedef __nv_bfloat16 bf16;
 
-__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
-    hi = __float2bfloat16_rn(v);
-    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+template <int NPL>
+__device__ __forceinline__ void split_store(float v, bf16* __restrict__ base, size_t idx, size_t plane_stride) {
+    const bf16 h = __float2bfloat16_rn(v);
+    base[idx] = h;
+    float r = v - __bfloat162float(h);
+    const bf16 m = __float2bfloat16_rn(r);
+    base[plane_stride + idx] = m;
+    if (NPL == 3) {
+        r -= __bfloat162float(m);
+        base[2 * plane_stride + idx] = __float2bfloat16_rn(r);
+    }
 }
 
 struct TapList { int k; int off[8]; };
 
-// x (B,C,T) fp32 -> dropout -> planes in (B,T,C) [forward operand] and, for the weight gradient, k time-shifted
-// copies in (k,B,C,T): bct[j][b][c][t] = xd[b][c][t + off_j] (zero outside [0,T)).  The shift is baked into the
-// copy because the weight-gradient GEMM contracts over t (its contiguous axis) and a TMA box cannot start at an
-// element offset that is not 16-byte aligned.  32(c) x 32(t) tile per CTA, block (32, 8).
-__global__ void split_input_kernel(const float* __restrict__ x, bf16* __restrict__ btc_hi,
-                                   bf16* __restrict__ btc_lo, bf16* __restrict__ bct_hi,
-                                   bf16* __restrict__ bct_lo, int Bn, int C, int T, float p,
+// x (B,C,T) fp32 -> dropout -> NPL planes in (B,T,Cp) [forward operand] and, for the weight gradient, 2 planes of k
+// time-shifted copies (k,B,C,T): xs[j][b][c][t] = xd[b][c][t + off_j] (zero outside [0,T)).  The shift is baked
+// into the copy because the weight-gradient GEMM contracts over t (its contiguous axis) and a TMA box cannot start
+// at an element offset that is not 16-byte aligned.  32(c) x 32(t) tile per CTA, block (32, 8).
+template <int NPL>
+__global__ void split_input_kernel(const float* __restrict__ x, bf16* __restrict__ btc, bf16* __restrict__ bct,
+                                   int Bn, int C, int Cp, int T, float p,
                                    const unsigned long long* __restrict__ seed_ptr, unsigned salt,
                                    const TapList taps) {
     __shared__ float tile[32][33];
     const DropCfg drop = make_drop(p, seed_ptr, salt);
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+    const size_t bct_plane = (size_t)taps.k * Bn * C * T;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int c = c0 + threadIdx.y + 8 * i, t = t0 + threadIdx.x;
@@ -35,44 +46,39 @@ __global__ void split_input_kernel(const float* __restrict__ x, bf16* __restrict
         if (c < C && t < T) {
             const size_t row = ((size_t)b * C + c) * T;
             v = x[row + t] * drop_scale(drop, (uint32_t)(row + t));
-            if (bct_hi) {
+            if (bct) {
                 for (int j = 0; j < taps.k; ++j) {
                     const int ts = t + taps.off[j];
                     float vs = 0.f;
                     if (ts >= 0 && ts < T) vs = (ts == t) ? v : x[row + ts] * drop_scale(drop, (uint32_t)(row + ts));
-                    bf16 h, l; split_bf16(vs, h, l);
-                    const size_t o = (((size_t)j * Bn + b) * C + c) * T + t;
-                    bct_hi[o] = h; bct_lo[o] = l;
+                    split_store<2>(vs, bct, (((size_t)j * Bn + b) * C + c) * T + t, bct_plane);
                 }
             }
         }
         tile[threadIdx.y + 8 * i][threadIdx.x] = v;
     }
     __syncthreads();
-    if (btc_hi) {
+    if (btc) {
+        const size_t btc_plane = (size_t)Bn * T * Cp;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
-            if (c < C && t < T) {
-                bf16 h, l;
-                split_bf16(tile[threadIdx.x][threadIdx.y + 8 * i], h, l);
-                const size_t o = ((size_t)b * T + t) * C + c;
-                btc_hi[o] = h; btc_lo[o] = l;
-            }
+            if (c < C && t < T)
+                split_store<NPL>(tile[threadIdx.x][threadIdx.y + 8 * i], btc, ((size_t)b * T + t) * Cp + c, btc_plane);
         }
     }
 }
 
-// gate backward (see conv.cu gate_bwd_kernel) producing dAB = [da ; db] directly as bf16 planes in
+// gate backward (see conv.cu gate_bwd_kernel) producing dAB = [da ; db] directly as 2 bf16 planes in
 // (B,T,2C) [data-gradient operand] and (B,2C,T) [weight-gradient operand]; dbias[2C] += sums over (b,t).
 __global__ void gate_bwd_split_kernel(const float* __restrict__ dy, const float* __restrict__ a,
                                       const float* __restrict__ s, const float* __restrict__ x,
-                                      bf16* __restrict__ btc_hi, bf16* __restrict__ btc_lo,
-                                      bf16* __restrict__ bct_hi, bf16* __restrict__ bct_lo,
-                                      float* __restrict__ dbias, int C, int T, int mode, int residual) {
+                                      bf16* __restrict__ btc, bf16* __restrict__ bct, float* __restrict__ dbias,
+                                      int Bn, int C, int T, int mode, int residual) {
     __shared__ float ta[32][33], tb[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
     const float gs = (mode == 0 && residual) ? 0.70710678118654752f : 1.f;
+    const size_t plane = (size_t)Bn * 2 * C * T;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int c = c0 + threadIdx.y + 8 * i, t = t0 + threadIdx.x;
@@ -82,12 +88,9 @@ __global__ void gate_bwd_split_kernel(const float* __restrict__ dy, const float*
             const float g = dy[in] * gs, av = a[in], sv = s[in];
             da = g * sv;
             db = g * ((mode == 0) ? av : (av - x[in])) * sv * (1.f - sv);
-            if (bct_hi) {
-                const size_t oa = ((size_t)b * 2 * C + c) * T + t, ob = oa + (size_t)C * T;
-                bf16 h, l;
-                split_bf16(da, h, l); bct_hi[oa] = h; bct_lo[oa] = l;
-                split_bf16(db, h, l); bct_hi[ob] = h; bct_lo[ob] = l;
-            }
+            const size_t oa = ((size_t)b * 2 * C + c) * T + t;
+            split_store<2>(da, bct, oa, plane);
+            split_store<2>(db, bct, oa + (size_t)C * T, plane);
         }
         ta[threadIdx.y + 8 * i][threadIdx.x] = da;
         tb[threadIdx.y + 8 * i][threadIdx.x] = db;
@@ -101,18 +104,52 @@ __global__ void gate_bwd_split_kernel(const float* __restrict__ dy, const float*
         const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
         if (c < C && t < T) {
             const size_t o = ((size_t)b * T + t) * 2 * C + c;
-            bf16 h, l;
-            split_bf16(ta[threadIdx.x][threadIdx.y + 8 * i], h, l); btc_hi[o] = h; btc_lo[o] = l;
-            split_bf16(tb[threadIdx.x][threadIdx.y + 8 * i], h, l); btc_hi[o + C] = h; btc_lo[o + C] = l;
+            split_store<2>(ta[threadIdx.x][threadIdx.y + 8 * i], btc, o, plane);
+            split_store<2>(tb[threadIdx.x][threadIdx.y + 8 * i], btc, o + C, plane);
         }
     }
 }
 
-// weight-norm pack for the tensor-core path: v (R=Cout, X=Cin, k) fp32, scale[R] = g/||v|| ->
-//   wb planes [k][Cout][Cin] (forward operand: rows co, K = ci) and wf planes [k][Cin][Cout] (dgrad: rows ci, K = co)
+// plain conv backward prologue: g = dy * (relu ? y > 0 : 1) -> 2 planes in (B,T,Cp) and (B,C,T); dbias[C] += sums.
+__global__ void grad_split_kernel(const float* __restrict__ dy, const float* __restrict__ y, bf16* __restrict__ btc,
+                                  bf16* __restrict__ bct, float* __restrict__ dbias, int Bn, int C, int Cp, int T,
+                                  int relu) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + threadIdx.y + 8 * i, t = t0 + threadIdx.x;
+        float g = 0.f;
+        if (c < C && t < T) {
+            const size_t in = ((size_t)b * C + c) * T + t;
+            g = dy[in];
+            if (relu && !(y[in] > 0.f)) g = 0.f;
+            if (bct) split_store<2>(g, bct, in, (size_t)Bn * C * T);
+        }
+        tile[threadIdx.y + 8 * i][threadIdx.x] = g;
+        const float sg = warp_sum(g);
+        if (threadIdx.x == 0 && c < C && dbias) atomicAdd(&dbias[c], sg);
+    }
+    __syncthreads();
+    if (btc) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
+            if (c < C && t < T)
+                split_store<2>(tile[threadIdx.x][threadIdx.y + 8 * i], btc, ((size_t)b * T + t) * Cp + c,
+                               (size_t)Bn * T * Cp);
+        }
+    }
+}
+
+// weight-norm pack: v [R][X][k] fp32, scale[R] = g/||v|| -> two plane sets with element (r,x,j) at
+// r*s_r + x*s_x + j*s_j: outA is written with lanes along (x,j) (choose the set whose unit stride is s_x),
+// outB with lanes along r (unit stride s_r).
+template <int NPLA, int NPLB>
 __global__ void wn_pack_split_kernel(const float* __restrict__ v, const float* __restrict__ scale,
-                                     bf16* __restrict__ wb_hi, bf16* __restrict__ wb_lo,
-                                     bf16* __restrict__ wf_hi, bf16* __restrict__ wf_lo, int R, int X, int k) {
+                                     bf16* __restrict__ outA, long long a_r, long long a_x, long long a_j,
+                                     long long a_plane, bf16* __restrict__ outB, long long b_r, long long b_x,
+                                     long long b_j, long long b_plane, int R, int X, int k) {
     __shared__ float tile[32][33];
     const int L = X * k;
     const int r0 = blockIdx.y * 32, e0 = blockIdx.x * 32;
@@ -123,21 +160,20 @@ __global__ void wn_pack_split_kernel(const float* __restrict__ v, const float* _
         if (r < R && e < L) {
             w = v[(size_t)r * L + e] * scale[r];
             const int xx = e / k, j = e - xx * k;
-            bf16 h, l; split_bf16(w, h, l);
-            const size_t o = ((size_t)j * R + r) * X + xx;
-            wb_hi[o] = h; wb_lo[o] = l;
+            if (outA) split_store<NPLA>(w, outA, (size_t)(r * a_r + xx * a_x + j * a_j), (size_t)a_plane);
         }
         tile[threadIdx.y + 8 * i][threadIdx.x] = w;
     }
     __syncthreads();
+    if (outB) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int e = e0 + threadIdx.y + 8 * i, r = r0 + threadIdx.x;
-        if (r < R && e < L) {
-            const int xx = e / k, j = e - xx * k;
-            bf16 h, l; split_bf16(tile[threadIdx.x][threadIdx.y + 8 * i], h, l);
-            const size_t o = ((size_t)j * X + xx) * R + r;
-            wf_hi[o] = h; wf_lo[o] = l;
+        for (int i = 0; i < 4; ++i) {
+            const int e = e0 + threadIdx.y + 8 * i, r = r0 + threadIdx.x;
+            if (r < R && e < L) {
+                const int xx = e / k, j = e - xx * k;
+                split_store<NPLB>(tile[threadIdx.x][threadIdx.y + 8 * i], outB,
+                                  (size_t)(r * b_r + xx * b_x + j * b_j), (size_t)b_plane);
+            }
         }
     }
 }
@@ -159,41 +195,92 @@ using namespace dv3;
 
 extern "C" {
 
-int dv3_tc_split_input(const float* x, void* btc_hi, void* btc_lo, void* bct_hi, void* bct_lo, int B, int C,
-                       int T, int k, int dilation, int causal, float p_drop, const unsigned long long* seed_ptr,
-                       unsigned salt, void* stream) {
+int dv3_tc_split_input(const float* x, void* btc, int npl, void* bct, int B, int C, int T, int k, int dilation,
+                       int causal, float p_drop, const unsigned long long* seed_ptr, unsigned salt, void* stream) {
     DV3_REQUIRE(B <= 65535 && (C + 31) / 32 <= 65535, "tc_split_input: grid too large");
     DV3_REQUIRE(k >= 1 && k <= 8, "tc_split_input: kernel size %d not in [1,8]", k);
+    DV3_REQUIRE(npl == 2 || npl == 3, "tc_split_input: npl must be 2 or 3");
     TapList taps;
     taps.k = k;
     const int padl = causal ? (k - 1) * dilation : (k - 1) / 2 * dilation;
     for (int j = 0; j < 8; ++j) taps.off[j] = j < k ? j * dilation - padl : 0;
+    const int Cp = (C + 7) / 8 * 8;
     dim3 grid((T + 31) / 32, (C + 31) / 32, B);
-    split_input_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, (bf16*)btc_hi, (bf16*)btc_lo,
-                                                                      (bf16*)bct_hi, (bf16*)bct_lo, B, C, T, p_drop,
-                                                                      seed_ptr, salt, taps);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (npl == 3)
+        split_input_kernel<3><<<grid, dim3(32, 8), 0, st>>>(x, (bf16*)btc, (bf16*)bct, B, C, Cp, T, p_drop, seed_ptr,
+                                                            salt, taps);
+    else
+        split_input_kernel<2><<<grid, dim3(32, 8), 0, st>>>(x, (bf16*)btc, (bf16*)bct, B, C, Cp, T, p_drop, seed_ptr,
+                                                            salt, taps);
     return check_launch("tc_split_input");
 }
 
-int dv3_tc_gate_bwd_split(const float* dy, const float* a, const float* s, const float* x, void* btc_hi,
-                          void* btc_lo, void* bct_hi, void* bct_lo, float* dbias, int B, int C, int T, int mode,
-                          int residual, void* stream) {
+int dv3_tc_gate_bwd_split(const float* dy, const float* a, const float* s, const float* x, void* btc, void* bct,
+                          float* dbias, int B, int C, int T, int mode, int residual, void* stream) {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B);
-    gate_bwd_split_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
-        dy, a, s, x, (bf16*)btc_hi, (bf16*)btc_lo, (bf16*)bct_hi, (bf16*)bct_lo, dbias, C, T, mode, residual);
+    gate_bwd_split_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dy, a, s, x, (bf16*)btc, (bf16*)bct, dbias,
+                                                                         B, C, T, mode, residual);
     return check_launch("tc_gate_bwd_split");
 }
 
-// v (Cout, Cin, k), g (Cout) -> bf16 planes wb [k][Cout][Cin], wf [k][Cin][Cout]; inv_norm, scale: [Cout] fp32.
-int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wb_hi, void* wb_lo,
-                          void* wf_hi, void* wf_lo, int Cout, int Cin, int k, void* stream) {
+int dv3_tc_grad_split(const float* dy, const float* y, void* btc, void* bct, float* dbias, int B, int C, int T,
+                      int relu, void* stream) {
+    const int Cp = (C + 7) / 8 * 8;
+    dim3 grid((T + 31) / 32, (C + 31) / 32, B);
+    grad_split_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dy, y, (bf16*)btc, (bf16*)bct, dbias, B, C, Cp,
+                                                                     T, relu);
+    return check_launch("tc_grad_split");
+}
+
+// Weight norm + split for a conv weight v (Cout, Cin, k), g [Cout]:
+//   wfwd: [npl][k][Cout][Cinp]  (forward operand: rows co, K = ci)     wbwd: [2][k][Cin][Coutp]  (data gradient)
+int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wfwd, int npl,
+                          void* wbwd, int Cout, int Cin, int k, void* stream) {
+    DV3_REQUIRE(npl == 2 || npl == 3, "tc_weightnorm_fwd: npl must be 2 or 3");
     cudaStream_t st = (cudaStream_t)stream;
     const int L = Cin * k;
+    const long long Cinp = (Cin + 7) / 8 * 8, Coutp = (Cout + 7) / 8 * 8;
     wn_norm_kernel2<<<(Cout * 32 + 255) / 256, 256, 0, st>>>(v, g, inv_norm, scale, Cout, L);
     if (int e = check_launch("tc_weightnorm_fwd(norm)")) return e;
-    wn_pack_split_kernel<<<dim3((L + 31) / 32, (Cout + 31) / 32), dim3(32, 8), 0, st>>>(
-        v, scale, (bf16*)wb_hi, (bf16*)wb_lo, (bf16*)wf_hi, (bf16*)wf_lo, Cout, Cin, k);
+    dim3 grid((L + 31) / 32, (Cout + 31) / 32);
+    if (npl == 3)
+        wn_pack_split_kernel<3, 2><<<grid, dim3(32, 8), 0, st>>>(v, scale, (bf16*)wfwd, Cinp, 1, (long long)Cout * Cinp,
+                                                              (long long)k * Cout * Cinp, (bf16*)wbwd, 1, Coutp,
+                                                              (long long)Cin * Coutp, (long long)k * Cin * Coutp,
+                                                              Cout, Cin, k);
+    else
+        wn_pack_split_kernel<2, 2><<<grid, dim3(32, 8), 0, st>>>(v, scale, (bf16*)wfwd, Cinp, 1, (long long)Cout * Cinp,
+                                                              (long long)k * Cout * Cinp, (bf16*)wbwd, 1, Coutp,
+                                                              (long long)Cin * Coutp, (long long)k * Cin * Coutp,
+                                                              Cout, Cin, k);
     return check_launch("tc_weightnorm_fwd(pack)");
+}
+
+// ConvTranspose1d(k=2,s=2) weight v (Cin, Cout, 2), g [Cin] (norm over dim 0 = Cin), run as a 1x1 conv with
+// 2*Cout output rows ordered (j, co):
+//   wfwd: [npl][2*Cout][Cinp]  rows (j,co), K = ci        wbwd: [2][Cin][K2p]  rows ci, K = (j,co), K2p = pad8(2*Cout)
+int dv3_tc_weightnorm_convt_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wfwd, int npl,
+                                void* wbwd, int Cin, int Cout, void* stream) {
+    DV3_REQUIRE(npl == 2 || npl == 3, "tc_weightnorm_convt_fwd: npl must be 2 or 3");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int L = Cout * 2;
+    const long long Cinp = (Cin + 7) / 8 * 8, K2p = (2 * Cout + 7) / 8 * 8;
+    wn_norm_kernel2<<<(Cin * 32 + 255) / 256, 256, 0, st>>>(v, g, inv_norm, scale, Cin, L);
+    if (int e = check_launch("tc_weightnorm_convt_fwd(norm)")) return e;
+    dim3 grid((L + 31) / 32, (Cin + 31) / 32);
+    // r = ci, x = co, j: outA (lanes along (x,j)) = wbwd [ci][j*Cout+co] ; outB (lanes along r) = wfwd [(j*Cout+co)][ci]
+    if (npl == 3)
+        wn_pack_split_kernel<2, 3><<<grid, dim3(32, 8), 0, st>>>(v, scale, (bf16*)wbwd, K2p, 1, (long long)Cout,
+                                                                 (long long)Cin * K2p, (bf16*)wfwd, 1, Cinp,
+                                                                 (long long)Cout * Cinp, (long long)2 * Cout * Cinp,
+                                                                 Cin, Cout, 2);
+    else
+        wn_pack_split_kernel<2, 2><<<grid, dim3(32, 8), 0, st>>>(v, scale, (bf16*)wbwd, K2p, 1, (long long)Cout,
+                                                                 (long long)Cin * K2p, (bf16*)wfwd, 1, Cinp,
+                                                                 (long long)Cout * Cinp, (long long)2 * Cout * Cinp,
+                                                                 Cin, Cout, 2);
+    return check_launch("tc_weightnorm_convt_fwd(pack)");
 }
 
 }  // extern "C"

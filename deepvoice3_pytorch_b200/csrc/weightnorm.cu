@@ -55,26 +55,64 @@ __global__ void wn_pack_kernel(const float* __restrict__ v, const float* __restr
     }
 }
 
-// backward, one warp per row:  dW = sum_s partial[s] ;  dot = <dW, v>
+// backward, one CTA (256 threads) per row:  dW = sum_s partial[s] ;  dot = <dW, v>
 //   dg = dot * inv_norm ;  dv = scale*dW - scale*dot*inv_norm^2 * v
-__global__ void wn_bwd_kernel(const float* __restrict__ dw_partials, long long split_stride, int nsplit,
-                              const float* __restrict__ v, const float* __restrict__ g,
-                              const float* __restrict__ inv_norm, float* __restrict__ dv,
-                              float* __restrict__ dg, int R, int L) {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (r >= R) return;
+// (one warp per row left the big layers -- 1024 rows x 1536 x up to 16 partials -- at 0.4 TB/s.)
+__global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ dw_partials, long long split_stride,
+                                                     int nsplit, const float* __restrict__ v,
+                                                     const float* __restrict__ g,
+                                                     const float* __restrict__ inv_norm, float* __restrict__ dv,
+                                                     float* __restrict__ dg, int R, int L) {
+    __shared__ float red[8];
+    __shared__ float s_dot;
+    const int r = blockIdx.x, tid = threadIdx.x;
     const size_t base = (size_t)r * L;
     float dot = 0.f;
-    for (int e = lane; e < L; e += 32) {
-        float d = 0.f;
-        for (int s = 0; s < nsplit; ++s) d += dw_partials[(size_t)s * split_stride + base + e];
-        dv[base + e] = d;                       // same thread re-reads it below
-        dot = fmaf(d, v[base + e], dot);
+    const bool vec = ((L & 3) == 0) && ((split_stride & 3) == 0);
+    if (vec) {
+        const int L4 = L >> 2;
+        for (int e = tid; e < L4; e += 256) {
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < nsplit; ++s) {
+                const float4 q = *reinterpret_cast<const float4*>(&dw_partials[(size_t)s * split_stride + base + 4 * e]);
+                d.x += q.x; d.y += q.y; d.z += q.z; d.w += q.w;
+            }
+            const float4 vv = *reinterpret_cast<const float4*>(&v[base + 4 * e]);
+            *reinterpret_cast<float4*>(&dv[base + 4 * e]) = d;
+            dot = fmaf(d.x, vv.x, dot); dot = fmaf(d.y, vv.y, dot); dot = fmaf(d.z, vv.z, dot); dot = fmaf(d.w, vv.w, dot);
+        }
+    } else {
+        for (int e = tid; e < L; e += 256) {
+            float d = 0.f;
+            for (int s = 0; s < nsplit; ++s) d += dw_partials[(size_t)s * split_stride + base + e];
+            dv[base + e] = d;
+            dot = fmaf(d, v[base + e], dot);
+        }
     }
     dot = warp_sum(dot);
+    if ((tid & 31) == 0) red[tid >> 5] = dot;
+    __syncthreads();
+    if (tid < 32) {
+        float t = tid < 8 ? red[tid] : 0.f;
+        t = warp_sum(t);
+        if (tid == 0) s_dot = t;
+    }
+    __syncthreads();
+    dot = s_dot;
     const float inv = inv_norm[r], sc = g[r] * inv, c2 = sc * dot * inv * inv;
-    for (int e = lane; e < L; e += 32) dv[base + e] = sc * dv[base + e] - c2 * v[base + e];
-    if (lane == 0) dg[r] = dot * inv;
+    // each thread rewrites exactly the elements it stored above
+    if (vec) {
+        const int L4 = L >> 2;
+        for (int e = tid; e < L4; e += 256) {
+            float4 d = *reinterpret_cast<float4*>(&dv[base + 4 * e]);
+            const float4 vv = *reinterpret_cast<const float4*>(&v[base + 4 * e]);
+            d.x = sc * d.x - c2 * vv.x; d.y = sc * d.y - c2 * vv.y; d.z = sc * d.z - c2 * vv.z; d.w = sc * d.w - c2 * vv.w;
+            *reinterpret_cast<float4*>(&dv[base + 4 * e]) = d;
+        }
+    } else {
+        for (int e = tid; e < L; e += 256) dv[base + e] = sc * dv[base + e] - c2 * v[base + e];
+    }
+    if (tid == 0) dg[r] = dot * inv;
 }
 
 }  // namespace dv3
@@ -101,7 +139,7 @@ int dv3_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* s
 int dv3_weightnorm_bwd(const float* dw_partials, long long split_stride, int nsplit, const float* v,
                        const float* g, const float* inv_norm, float* dv, float* dg, int R, int X, int k,
                        void* stream) {
-    wn_bwd_kernel<<<ceil_div(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+    wn_bwd_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(
         dw_partials, split_stride, nsplit, v, g, inv_norm, dv, dg, R, X * k);
     return check_launch("weightnorm_bwd");
 }

@@ -15,8 +15,11 @@ MODE_GLU, MODE_HIGHWAY = 0, 1
 
 # Arithmetic of the ConvBlock contractions:
 #   "fp32"   exact-fp32 CUDA-core kernels (csrc/conv.cu)
-#   "bf16x3" tcgen05 tensor cores with split-bf16 operands, fp32-equivalent accuracy (csrc/tc_gemm.cu); shapes the
-#            tensor-core kernels do not cover (C % 128 != 0, T % 8 != 0) still run on the fp32 kernels.
+#   "tc"     tcgen05 tensor cores with split-bf16 operands (csrc/tc_gemm.cu): forward GEMMs with 3 planes / 6 products
+#            (fp32-equivalent, full-depth outputs stay inside rtol 1e-3 / atol 1e-4), backward GEMMs with 2 planes /
+#            3 products (~1e-5 per block).  Shapes the tensor-core kernels do not cover (C % 128 != 0, T % 8 != 0, tiny
+#            GEMMs) still run on the fp32 kernels.
+#   "bf16x3" as "tc" but 2 planes / 3 products in the forward too (fastest; ~1e-5 per block, ~2e-4 at full depth)
 conv_math = os.environ.get("DV3_CONV_MATH", "fp32")
 
 
@@ -177,8 +180,17 @@ class _ConvBlockFn(torch.autograd.Function):
         return dx, dv, dg, dbias, dspk, None, None, None, None, None, None, None
 
 
+def _fwd_planes():
+    """Planes per operand in FORWARD GEMMs: 3 ("x6", fp32-equivalent) in strict "tc" mode, 2 ("x3") in "bf16x3"."""
+    return 3 if conv_math == "tc" else 2
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
 class _ConvBlockTCFn(torch.autograd.Function):
-    """Same contract as _ConvBlockFn on the tcgen05 path: operands are pre-split into bf16 hi/lo planes."""
+    """Same contract as _ConvBlockFn on the tcgen05 path: operands are pre-split into bf16 planes."""
 
     @staticmethod
     def forward(ctx, x, v, g, bias, spk, k, dilation, causal, mode, residual, p_drop, training):
@@ -186,32 +198,32 @@ class _ConvBlockTCFn(torch.autograd.Function):
         B, C, T = x.shape
         dev = x.device
         bf = torch.bfloat16
+        npl = _fwd_planes()
         need_bwd = any(ctx.needs_input_grad)
         inv = torch.empty(2 * C, device=dev)
         scale = torch.empty_like(inv)
-        wb = torch.empty(2, k, 2 * C, C, device=dev, dtype=bf)       # [hi|lo][k][2C][C]
-        wf = torch.empty(2, k, C, 2 * C, device=dev, dtype=bf)       # [hi|lo][k][C][2C]
-        lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wb[0]), _p(wb[1]), _p(wf[0]),
-                 _p(wf[1]), 2 * C, C, k, _stream())
+        wfwd = torch.empty(npl, k, 2 * C, C, device=dev, dtype=bf)
+        wbwd = torch.empty(2, k, C, 2 * C, device=dev, dtype=bf)
+        lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), npl, _p(wbwd), 2 * C, C, k,
+                 _stream())
         p, seed_ptr, salt = _drop_args(p_drop, training, dev)
-        x_btc = torch.empty(2, B, T, C, device=dev, dtype=bf)
+        x_btc = torch.empty(npl, B, T, C, device=dev, dtype=bf)
         x_bct = torch.empty(2, k, B, C, T, device=dev, dtype=bf) if need_bwd else None   # k shifted copies
-        lib.call("dv3_tc_split_input", _p(x), _p(x_btc[0]), _p(x_btc[1]),
-                 _p(x_bct[0]) if need_bwd else None, _p(x_bct[1]) if need_bwd else None, B, C, T, k, dilation,
-                 int(causal), p, seed_ptr, salt, _stream())
+        lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, C, T, k, dilation, int(causal), p,
+                 seed_ptr, salt, _stream())
         y = torch.empty_like(x)
         a = torch.empty_like(x) if need_bwd else None
         s = torch.empty_like(x) if need_bwd else None
-        lib.call("dv3_tc_convblock_fwd", _p(x_btc[0]), _p(x_btc[1]), _p(wb[0]), _p(wb[1]), _p(bias), _p(spk),
-                 _p(x), _p(y), _p(a), _p(s), B, C, T, k, dilation, int(causal), mode, int(residual), _stream())
+        lib.call("dv3_tc_convblock_fwd", _p(x_btc), _p(wfwd), npl, _p(bias), _p(spk), _p(x), _p(y), _p(a), _p(s),
+                 B, C, T, k, dilation, int(causal), mode, int(residual), _stream())
         if need_bwd:
-            ctx.save_for_backward(x, v, g, a, s, x_bct, wf, inv)
+            ctx.save_for_backward(x, v, g, a, s, x_bct, wbwd, inv)
             ctx.cfg = (k, dilation, causal, mode, residual, p, salt, spk is not None, dev)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, v, g, a, s, x_bct, wf, inv = ctx.saved_tensors
+        x, v, g, a, s, x_bct, wbwd, inv = ctx.saved_tensors
         k, dilation, causal, mode, residual, p, salt, has_spk, dev = ctx.cfg
         seed_ptr = _p(rng.seed_tensor(dev)) if p > 0 else None
         dy = _c(dy)
@@ -220,8 +232,8 @@ class _ConvBlockTCFn(torch.autograd.Function):
         d_btc = torch.empty(2, B, T, 2 * C, device=dev, dtype=bf)
         d_bct = torch.empty(2, B, 2 * C, T, device=dev, dtype=bf)
         dbias = torch.zeros(2 * C, device=dev)
-        lib.call("dv3_tc_gate_bwd_split", _p(dy), _p(a), _p(s), _p(x), _p(d_btc[0]), _p(d_btc[1]), _p(d_bct[0]),
-                 _p(d_bct[1]), _p(dbias), B, C, T, mode, int(residual), _stream())
+        lib.call("dv3_tc_gate_bwd_split", _p(dy), _p(a), _p(s), _p(x), _p(d_btc), _p(d_bct), _p(dbias), B, C, T,
+                 mode, int(residual), _stream())
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
@@ -229,20 +241,155 @@ class _ConvBlockTCFn(torch.autograd.Function):
                 addmode, e1, e2, alpha = (1, dy, None, 0.7071067811865476) if residual else (0, None, None, 0.0)
             else:
                 addmode, e1, e2, alpha = 2, dy, s, 0.0
-            lib.call("dv3_tc_conv_dgrad", _p(d_btc[0]), _p(d_btc[1]), _p(wf[0]), _p(wf[1]), _p(dx), B, C, T, k,
-                     dilation, int(causal), p, seed_ptr, salt, addmode, _p(e1), _p(e2), alpha, _stream())
+            lib.call("dv3_tc_conv", _p(d_btc), _p(wbwd), 2, _p(dx), B, 2 * C, C, T, k, dilation, int(causal), 1,
+                     None, 0, p, seed_ptr, salt, addmode, _p(e1), _p(e2), alpha, _stream())
         dv = dg = None
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            nsplit = lib.raw("dv3_tc_conv_wgrad_nsplit")(B, C, T, k)
+            nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, 2 * C, C, T, k)
             numel = v.numel()
             partials = torch.empty(nsplit, numel, device=dev)
-            lib.call("dv3_tc_conv_wgrad", _p(d_bct[0]), _p(d_bct[1]), _p(x_bct[0]), _p(x_bct[1]), _p(partials),
-                     numel, B, C, T, k, dilation, int(causal), _stream())
+            lib.call("dv3_tc_wgrad", _p(d_bct), _p(x_bct), _p(partials), numel, B, 2 * C, C, T, k, 2 * C, C * k, 0,
+                     k, 1, _stream())
             dv, dg = _wn_bwd(partials, nsplit, v, g, inv)
         dspk = None
         if has_spk and ctx.needs_input_grad[4]:
             dspk = d_bct[0, :, :C, :].float() + d_bct[1, :, :C, :].float()
         return dx, dv, dg, dbias, dspk, None, None, None, None, None, None, None
+
+
+class _Conv1dTCFn(torch.autograd.Function):
+    """Plain weight-normed conv (+ReLU) on the tcgen05 path (1x1 convs, projections)."""
+
+    @staticmethod
+    def forward(ctx, x, v, g, bias, k, dilation, causal, relu):
+        _chk(x, v, g, bias)
+        B, Cin, T = x.shape
+        Cout = v.shape[0]
+        dev, bf = x.device, torch.bfloat16
+        npl = _fwd_planes()
+        need_bwd = any(ctx.needs_input_grad)
+        Cinp, Coutp = _pad8(Cin), _pad8(Cout)
+        inv = torch.empty(Cout, device=dev)
+        scale = torch.empty_like(inv)
+        wfwd = torch.empty(npl, k, Cout, Cinp, device=dev, dtype=bf)
+        wbwd = torch.empty(2, k, Cin, Coutp, device=dev, dtype=bf)
+        lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), npl, _p(wbwd), Cout, Cin, k,
+                 _stream())
+        x_btc = torch.empty(npl, B, T, Cinp, device=dev, dtype=bf)
+        need_w = need_bwd and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        x_bct = torch.empty(2, k, B, Cin, T, device=dev, dtype=bf) if need_w else None
+        lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, Cin, T, k, dilation, int(causal), 0.0,
+                 None, 0, _stream())
+        y = torch.empty(B, Cout, T, device=dev)
+        lib.call("dv3_tc_conv", _p(x_btc), _p(wfwd), npl, _p(y), B, Cin, Cout, T, k, dilation, int(causal), 0,
+                 _p(bias), int(relu), 0.0, None, 0, 0, None, None, 0.0, _stream())
+        if need_bwd:
+            ctx.save_for_backward(v, g, x_bct, wbwd, inv, y if relu else None)
+            ctx.cfg = (B, Cin, Cout, T, k, dilation, causal, relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        v, g, x_bct, wbwd, inv, y = ctx.saved_tensors
+        B, Cin, Cout, T, k, dilation, causal, relu = ctx.cfg
+        dy = _c(dy)
+        dev, bf = dy.device, torch.bfloat16
+        Coutp = _pad8(Cout)
+        need_x = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        g_btc = torch.empty(2, B, T, Coutp, device=dev, dtype=bf) if need_x else None
+        g_bct = torch.empty(2, B, Cout, T, device=dev, dtype=bf) if need_w else None
+        dbias = torch.zeros(Cout, device=dev)
+        lib.call("dv3_tc_grad_split", _p(dy), _p(y), _p(g_btc), _p(g_bct), _p(dbias), B, Cout, T, int(relu), _stream())
+        dx = None
+        if need_x:
+            dx = torch.empty(B, Cin, T, device=dev)
+            lib.call("dv3_tc_conv", _p(g_btc), _p(wbwd), 2, _p(dx), B, Cout, Cin, T, k, dilation, int(causal), 1, None,
+                     0, 0.0, None, 0, 0, None, None, 0.0, _stream())
+        dv = dg = None
+        if need_w:
+            nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, Cout, Cin, T, k)
+            numel = v.numel()
+            partials = torch.empty(nsplit, numel, device=dev)
+            lib.call("dv3_tc_wgrad", _p(g_bct), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, Cout, Cin * k, 0, k,
+                     1, _stream())
+            dv, dg = _wn_bwd(partials, nsplit, v, g, inv)
+        return dx, dv, dg, dbias, None, None, None, None
+
+
+class _ConvT2TCFn(torch.autograd.Function):
+    """ConvTranspose1d(k=2,s=2) on the tcgen05 path: a 1x1 conv with 2*Cout rows (j,co) + the time interleave."""
+
+    @staticmethod
+    def forward(ctx, x, v, g, bias):
+        _chk(x, v, g, bias)
+        B, Cin, T = x.shape
+        Cout = v.shape[1]
+        dev, bf = x.device, torch.bfloat16
+        npl = _fwd_planes()
+        Cinp, K2p = _pad8(Cin), _pad8(2 * Cout)
+        inv = torch.empty(Cin, device=dev)
+        scale = torch.empty_like(inv)
+        wfwd = torch.empty(npl, 2 * Cout, Cinp, device=dev, dtype=bf)
+        wbwd = torch.empty(2, Cin, K2p, device=dev, dtype=bf)
+        lib.call("dv3_tc_weightnorm_convt_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), npl, _p(wbwd), Cin, Cout,
+                 _stream())
+        x_btc = torch.empty(npl, B, T, Cinp, device=dev, dtype=bf)
+        x_bct = torch.empty(2, 1, B, Cin, T, device=dev, dtype=bf)
+        lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, Cin, T, 1, 1, 0, 0.0, None, 0, _stream())
+        bias2 = bias.repeat(2)
+        yp = torch.empty(B, 2 * Cout, T, device=dev)
+        lib.call("dv3_tc_conv", _p(x_btc), _p(wfwd), npl, _p(yp), B, Cin, 2 * Cout, T, 1, 1, 0, 0, _p(bias2), 0, 0.0,
+                 None, 0, 0, None, None, 0.0, _stream())
+        y = torch.empty(B, Cout, 2 * T, device=dev)
+        lib.call("dv3_interleave2", _p(yp), _p(y), B, Cout, T, 0, _stream())
+        ctx.save_for_backward(v, g, x_bct, wbwd, inv)
+        ctx.cfg = (B, Cin, Cout, T)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        v, g, x_bct, wbwd, inv = ctx.saved_tensors
+        B, Cin, Cout, T = ctx.cfg
+        dy = _c(dy)
+        dev, bf = dy.device, torch.bfloat16
+        K2p = _pad8(2 * Cout)
+        dyp = torch.empty(B, 2 * Cout, T, device=dev)
+        lib.call("dv3_interleave2", _p(dy), _p(dyp), B, Cout, T, 1, _stream())
+        g_btc = torch.empty(2, B, T, K2p, device=dev, dtype=bf)
+        g_bct = torch.empty(2, B, 2 * Cout, T, device=dev, dtype=bf)
+        db2 = torch.zeros(2 * Cout, device=dev)
+        lib.call("dv3_tc_grad_split", _p(dyp), None, _p(g_btc), _p(g_bct), _p(db2), B, 2 * Cout, T, 0, _stream())
+        dbias = db2[:Cout] + db2[Cout:]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, Cin, T, device=dev)
+            lib.call("dv3_tc_conv", _p(g_btc), _p(wbwd), 2, _p(dx), B, 2 * Cout, Cin, T, 1, 1, 0, 1, None, 0, 0.0, None,
+                     0, 0, None, None, 0.0, _stream())
+        dv = dg = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            M = 2 * Cout
+            nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, M, Cin, T, 1)
+            numel = v.numel()
+            partials = torch.empty(nsplit, numel, device=dev)
+            # element (m=(j,co), ci) -> v layout (ci, co, j): ci*2*Cout + co*2 + j
+            lib.call("dv3_tc_wgrad", _p(g_bct), _p(x_bct), _p(partials), numel, B, M, Cin, T, 1, Cout, 2, 1, 2 * Cout,
+                     0, _stream())
+            dv, dg = _wn_bwd(partials, nsplit, v, g, inv)
+        return dx, dv, dg, dbias
+
+
+def _use_tc_conv(x, Cin, Cout, k):
+    """Tensor cores for plain convs when the mode asks for it, the shape is supported and the GEMM is big enough to
+    amortise the operand-split passes."""
+    if conv_math not in ("tc", "bf16x3") or not x.is_cuda:
+        return False
+    B, _, T = x.shape
+    if not lib.raw("dv3_tc_conv_supported")(B, Cin, Cout, T, int(k)):
+        return False
+    if k > 1 and Cin % 128 != 0:          # the data gradient swaps the roles of Cin / Cout
+        return False
+    return min(Cin, Cout) >= 32 and B * T >= 512
 
 
 def tc_supported(B, C, T, k):
@@ -253,9 +400,9 @@ def convblock(x, v, g, bias, spk=None, k=3, dilation=1, causal=False, mode=MODE_
               p_drop=0.0, training=False):
     """Fused weight-normed dilated conv + gate.  x (B,C,T); v (2C,C,k); g (2C,1,1); bias (2C);
     spk (B,C,T) already softsign'ed (or None)."""
-    if conv_math == "bf16x3" and x.is_cuda and tc_supported(x.shape[0], x.shape[1], x.shape[2], int(k)):
+    if conv_math in ("tc", "bf16x3") and x.is_cuda and tc_supported(x.shape[0], x.shape[1], x.shape[2], int(k)):
         fn = _ConvBlockTCFn
-    elif conv_math in ("fp32", "bf16x3"):
+    elif conv_math in ("fp32", "bf16x3", "tc"):
         fn = _ConvBlockFn
     else:
         raise Dv3Error("unknown conv_math %r" % (conv_math,))
@@ -306,7 +453,8 @@ class _Conv1dFn(torch.autograd.Function):
 
 def conv1d(x, v, g, bias, k=1, dilation=1, causal=False, relu=False):
     """Weight-normed Conv1d with 'same' (or causal) padding, optional fused ReLU.  x (B,Cin,T)."""
-    return _Conv1dFn.apply(_c(x), v, g, bias, int(k), int(dilation), bool(causal), bool(relu))
+    fn = _Conv1dTCFn if _use_tc_conv(x, v.shape[1], v.shape[0], k) else _Conv1dFn
+    return fn.apply(_c(x), v, g, bias, int(k), int(dilation), bool(causal), bool(relu))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -500,7 +648,8 @@ class _ConvT2Fn(torch.autograd.Function):
 
 
 def conv_transpose1d_k2s2(x, v, g, bias):
-    return _ConvT2Fn.apply(_c(x), v, g, bias)
+    fn = _ConvT2TCFn if _use_tc_conv(x, v.shape[0], 2 * v.shape[1], 1) else _ConvT2Fn
+    return fn.apply(_c(x), v, g, bias)
 
 
 def linear(x, v, g, bias):

@@ -140,38 +140,47 @@ int dv3_stft_mel(const float* wav, const int* lengths, const float* mel_basis, c
                  const int* mel_len, float* linear, float* mel, int nclips, int max_len, int max_frames,
                  int n_mels, float preemph, float min_level_db, float ref_level_db, void* stream);
 
-/* ================= tensor-core ("bf16x3") ConvBlock path: tcgen05 + TMA, fp32-equivalent accuracy =================
- * Same reference code as dv3_convblock_fwd / dv3_conv1d_dgrad / dv3_conv1d_wgrad (modules.py:145-164, 200-226 and
- * their autograd), computed as hi*hi + hi*lo + lo*hi over bf16 planes hi = bf16(x), lo = bf16(x - hi).
- * Plane pointers are bf16 device buffers.  Supported when dv3_tc_supported(B, C, T, k) returns 1
- * (C % 128 == 0, T % 8 == 0, k <= 8); callers use the exact-fp32 entry points otherwise. */
-int dv3_tc_supported(int B, int C, int T, int k);
-/* x (B,C,T) fp32 -> conv-input dropout -> planes in (B,T,C) (forward operand) and k time-shifted copies (k,B,C,T),
- * copy j = input shifted by tap j's offset, zero padded (weight-gradient operand; pass NULL for both bct pointers
- * to skip). */
-int dv3_tc_split_input(const float* x, void* btc_hi, void* btc_lo, void* bct_hi, void* bct_lo, int B, int C,
-                       int T, int k, int dilation, int causal, float p_drop, const unsigned long long* seed_ptr,
-                       unsigned salt, void* stream);
-/* weight norm + split: v (Cout,Cin,k), g [Cout] -> planes wb [k][Cout][Cin] (forward) and wf [k][Cin][Cout] (dgrad). */
-int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wb_hi, void* wb_lo,
-                          void* wf_hi, void* wf_lo, int Cout, int Cin, int k, void* stream);
-int dv3_tc_convblock_fwd(const void* xd_hi, const void* xd_lo, const void* w_hi, const void* w_lo,
-                         const float* bias, const float* spk, const float* res, float* y, float* save_a,
-                         float* save_s, int B, int C, int T, int k, int dilation, int causal, int mode,
-                         int residual, void* stream);
-/* gate backward writing dAB = [da ; db] as planes in (B,T,2C) (dgrad operand) and (B,2C,T) (wgrad operand). */
-int dv3_tc_gate_bwd_split(const float* dy, const float* a, const float* s, const float* x, void* btc_hi,
-                          void* btc_lo, void* bct_hi, void* bct_lo, float* dbias, int B, int C, int T, int mode,
-                          int residual, void* stream);
-int dv3_tc_conv_dgrad(const void* dab_hi, const void* dab_lo, const void* w_hi, const void* w_lo, float* dx,
-                      int B, int C, int T, int k, int dilation, int causal, float p_drop,
-                      const unsigned long long* seed_ptr, unsigned salt, int addmode, const float* e1,
-                      const float* e2, float alpha, void* stream);
-int dv3_tc_conv_wgrad_nsplit(int B, int C, int T, int k);
-/* xd_hi/lo here are the (k,B,C,T) shifted copies written by dv3_tc_split_input */
-int dv3_tc_conv_wgrad(const void* dab_hi, const void* dab_lo, const void* xd_hi, const void* xd_lo,
-                      float* dw_partials, long long split_stride, int B, int C, int T, int k, int dilation,
-                      int causal, void* stream);
+/* ================= tensor-core ConvBlock / conv path: tcgen05 + TMA, split-bf16 operands =================
+ * Same reference code as dv3_convblock_fwd / dv3_conv1d_fwd / dv3_conv1d_dgrad / dv3_conv1d_wgrad (modules.py:94-100,
+ * 145-164, 200-226 and their autograd).  fp32 operands are split into bf16 planes p0 = bf16(x), p1 = bf16(x-p0)
+ * [, p2 = bf16(x-p0-p1)]; npl = 2 issues p0*p0 + p0*p1 + p1*p0 ("x3", ~2^-17/operand), npl = 3 adds
+ * p1*p1 + p0*p2 + p2*p0 ("x6", fp32-equivalent).  Plane buffers are bf16 device memory laid out [npl][...]; channel
+ * pitches are padded to a multiple of 8.  Callers use the exact-fp32 entry points for unsupported shapes. */
+int dv3_tc_k_block(void);                                   /* K-block width in use: 32 (default) or 64 (DV3_TC_BK=64) */
+int dv3_tc_supported(int B, int C, int T, int k);           /* gated block: C % 128 == 0, T % 8 == 0, k <= 8 */
+int dv3_tc_conv_supported(int B, int Cin, int Cout, int T, int k);   /* plain conv: T % 8 == 0, (k == 1 or Cout % 128 == 0) */
+/* x (B,C,T) fp32 -> conv-input dropout -> btc: [npl][B][T][Cp] planes (forward operand, Cp = pad8(C)) and
+ * bct: [2][k][B][C][T] planes = k time-shifted zero-padded copies (weight-gradient operand; NULL to skip). */
+int dv3_tc_split_input(const float* x, void* btc, int npl, void* bct, int B, int C, int T, int k, int dilation,
+                       int causal, float p_drop, const unsigned long long* seed_ptr, unsigned salt, void* stream);
+/* gate backward writing dAB = [da ; db] as planes btc: [2][B][T][2C] (dgrad operand), bct: [2][B][2C][T] (wgrad). */
+int dv3_tc_gate_bwd_split(const float* dy, const float* a, const float* s, const float* x, void* btc, void* bct,
+                          float* dbias, int B, int C, int T, int mode, int residual, void* stream);
+/* plain-conv backward prologue: g = dy*(relu ? y>0 : 1) -> btc: [2][B][T][Cp], bct: [2][B][C][T]; dbias[C] += sums. */
+int dv3_tc_grad_split(const float* dy, const float* y, void* btc, void* bct, float* dbias, int B, int C, int T,
+                      int relu, void* stream);
+/* weight norm + split: v (Cout,Cin,k), g [Cout] -> wfwd: [npl][k][Cout][Cinp] (forward), wbwd: [2][k][Cin][Coutp] (dgrad). */
+int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wfwd, int npl,
+                          void* wbwd, int Cout, int Cin, int k, void* stream);
+/* ConvTranspose1d(k=2,s=2) weight v (Cin,Cout,2), g [Cin] as a 1x1 conv with 2*Cout rows ordered (j,co):
+ * wfwd: [npl][2*Cout][Cinp], wbwd: [2][Cin][pad8(2*Cout)]. */
+int dv3_tc_weightnorm_convt_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wfwd, int npl,
+                                void* wbwd, int Cin, int Cout, void* stream);
+/* gated forward: xd = btc planes of dv3_tc_split_input, w = wfwd planes [npl][k][2C][C]. */
+int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bias, const float* spk,
+                         const float* res, float* y, float* save_a, float* save_s, int B, int C, int T, int k,
+                         int dilation, int causal, int mode, int residual, void* stream);
+/* generic conv / data gradient: out (B,Nc,T) = sum_j A[b,t+off_j,:].W[j,n,:], then *dropmask, +bias, +addend, relu.
+ * a: [npl][B][T][pad8(Kc)], w: [npl][k][Nc][pad8(Kc)]; transpose_taps = 1 for a data gradient. */
+int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc, int Nc, int T, int k, int dilation,
+                int causal, int transpose_taps, const float* bias, int relu, float p_drop,
+                const unsigned long long* seed_ptr, unsigned salt, int addmode, const float* e1, const float* e2,
+                float alpha, void* stream);
+/* weight gradient: dy: [2][B][Mw][T], xs: [2][k][B][Nw][T]; partial element (m,n,j) at
+ * (m%msplit)*s_m + (m/msplit)*s_mh + n*s_n + j*s_j; writes dv3_tc_wgrad_nsplit(...) partials. */
+int dv3_tc_wgrad_nsplit(int B, int Mw, int Nw, int T, int k);
+int dv3_tc_wgrad(const void* dy, const void* xs, float* dw_partials, long long split_stride, int B, int Mw, int Nw,
+                 int T, int k, int msplit, long long s_m, long long s_mh, long long s_n, long long s_j, void* stream);
 
 #ifdef __cplusplus
 }
