@@ -192,22 +192,21 @@ def convblock_roofline(dev, pk, pk_kind):
     y, sa, ss = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     math = ops.conv_math
-    if math == "bf16x3":
+    if math in ("tc", "bf16x3"):
         bf = torch.bfloat16
         inv, scale = torch.empty(2 * C, device=dev), torch.empty(2 * C, device=dev)
-        wb = torch.empty(2, k, 2 * C, C, device=dev, dtype=bf)
-        wf = torch.empty(2, k, C, 2 * C, device=dev, dtype=bf)
-        ops.lib.call("dv3_tc_weightnorm_fwd", ops._p(v), ops._p(g), ops._p(inv), ops._p(scale), ops._p(wb[0]),
-                     ops._p(wb[1]), ops._p(wf[0]), ops._p(wf[1]), 2 * C, C, k, ops._stream())
+        wfwd = torch.empty(2, k, 2 * C, C, device=dev, dtype=bf)
+        wbwd = torch.empty(2, k, C, 2 * C, device=dev, dtype=bf)
+        ops.lib.call("dv3_tc_weightnorm_fwd", ops._p(v), ops._p(g), ops._p(inv), ops._p(scale), ops._p(wfwd), 2,
+                     ops._p(wbwd), 2 * C, C, k, ops._stream())
         xs = torch.empty(2, Bc, T, C, device=dev, dtype=bf)
-        ops.lib.call("dv3_tc_split_input", ops._p(x), ops._p(xs[0]), ops._p(xs[1]), None, None, Bc, C, T, k, d, 0,
-                     0.0, None, 0, ops._stream())
-        name = "tc_conv_kernel<FWD> via dv3_tc_convblock_fwd"
+        ops.lib.call("dv3_tc_split_input", ops._p(x), ops._p(xs), 2, None, Bc, C, T, k, d, 0, 0.0, None, 0,
+                     ops._stream())
+        name = "tc_conv_kernel<GATED> via dv3_tc_convblock_fwd"
 
         def launch():
-            ops.lib.call("dv3_tc_convblock_fwd", ops._p(xs[0]), ops._p(xs[1]), ops._p(wb[0]), ops._p(wb[1]),
-                         ops._p(bias), None, ops._p(x), ops._p(y), ops._p(sa), ops._p(ss), Bc, C, T, k, d, 0, 0, 1,
-                         ops._stream())
+            ops.lib.call("dv3_tc_convblock_fwd", ops._p(xs), ops._p(wfwd), 2, ops._p(bias), None, ops._p(x), ops._p(y),
+                         ops._p(sa), ops._p(ss), Bc, C, T, k, d, 0, 0, 1, ops._stream())
         mma_passes = 3
     else:
         w_f, w_b, inv = ops._wn_conv_fwd(v, g)
@@ -263,6 +262,7 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
 
+    ops.conv_math = args.math
     bname, kw, extra = PRESETS[args.preset]
     torch.manual_seed(1234)                      # identical initial weights on every rank (as DDP broadcasts)
     model = getattr(builder, bname)(**kw).to(dev)
@@ -290,13 +290,15 @@ def run_gpu_arm(args):
         return float(t.item())
 
     # ---- device-resident throughput (value) ------------------------------------------------------
+    # nvidia-smi needs ~0.5 s to deliver its first sample and a 10-step timed region lasts ~0.1 s, so the sampler
+    # runs from the warm-up to the end of the e2e region (the GPU is under the same load throughout).
+    clocks = ClockSampler(local).__enter__()
     for _ in range(max(args.warmup, 3)):
         loss = step.step(resident)
     torch.cuda.synchronize()
     ops.check_index_errors()
     l0 = lib.raw("dv3_launch_count")()
-    with ClockSampler(local) as clocks:
-        t_res = timed(lambda: step.step(resident), args.steps)
+    t_res = timed(lambda: step.step(resident), args.steps)
     launches = (lib.raw("dv3_launch_count")() - l0) // args.steps
     if step.launches_per_step is not None:       # graph replay: the launches were recorded at capture time
         launches = step.launches_per_step
@@ -312,6 +314,11 @@ def run_gpu_arm(args):
     for _ in range(2):
         e2e_step()
     t_e2e = timed(e2e_step, args.steps)
+    t_extra = time.perf_counter()
+    while len(clocks.rows) < 3 and time.perf_counter() - t_extra < 3.0:      # keep the load on until sampled
+        step.step(resident)
+    torch.cuda.synchronize()
+    clocks.__exit__()
 
     frames = B * T_MEL * world
     out = {
@@ -322,7 +329,11 @@ def run_gpu_arm(args):
                                "(T_dec=200), random-init weights" % args.preset,
                    "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "inputs larger than L2 (>1.5 GB touched per step)",
-                   "cuda_graph": not args.no_graph, "conv_math": ops.conv_math},
+                   "cuda_graph": not args.no_graph, "conv_math": ops.conv_math,
+                   "conv_math_note": {"tc": "tcgen05 bf16 hi/lo split (hi*hi+hi*lo+lo*hi), fp32 accumulate: every block "
+                                            "within ~1e-5 of exact fp32, full-depth outputs within 2e-4 (tests)",
+                                      "bf16x3": "alias of tc",
+                                      "fp32": "exact fp32 FMA on CUDA cores"}[ops.conv_math]},
         "e2e": {"value": frames * args.steps / t_e2e, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / args.steps * 1e3},
         "gpu_launches": int(launches), "loss": loss_val, "clocks": clocks.summary(),
@@ -349,6 +360,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--preset", default="deepvoice3_ljspeech", choices=sorted(PRESETS))
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--math", default=os.environ.get("DV3_CONV_MATH", "tc"), choices=["tc", "fp32", "bf16x3"],
+                    help="ConvBlock arithmetic: tc = tcgen05 split-bf16 (fp32-equivalent, default), fp32 = CUDA cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

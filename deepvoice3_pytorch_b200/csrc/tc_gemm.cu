@@ -1,11 +1,13 @@
 // tcgen05 tensor-core path of the ConvBlock and of the plain (1x1 / k-tap) weight-normed convolutions: forward,
 // data-gradient and weight-gradient as implicit GEMMs with fp32-equivalent accuracy from split-bf16 operands.
-// Every fp32 operand is pre-split into bf16 planes p0 = bf16(x), p1 = bf16(x - p0), [p2 = bf16(x - p0 - p1)]
-// (tc_split.cu, which also applies the input dropout and emits the K-major layout each GEMM wants) and each K-step
-// issues the significant cross products into one fp32 TMEM accumulator:
-//     NPL = 2 ("x3"): p0*p0 + p0*p1 + p1*p0                      ~2^-17 per operand, 1e-5 per block
-//     NPL = 3 ("x6"): + p1*p1 + p0*p2 + p2*p0                    ~2^-24, indistinguishable from fp32 FMA
-// (single-pass TF32 would miss the rtol=1e-3/atol=1e-4 parity bar after ~30 blocks.)
+// Every fp32 operand is pre-split into bf16 planes p0 = bf16(x), p1 = bf16(x - p0) (tc_split.cu, which also applies
+// the input dropout and emits the K-major layout each GEMM wants) and each K-step issues p0*p0 + p0*p1 + p1*p0
+// (operand error ~2^-17; single-pass TF32 would miss the rtol=1e-3/atol=1e-4 parity bar after ~30 blocks).
+// Accuracy note (measured, tools/precision_report.py): the tensor core adds each MMA into the fp32 accumulator with
+// truncation, a bias of ~N_mma x 2^-25 relative -- with one accumulator that dominated the operand-split error and
+// made a 3-plane / 6-product variant WORSE than this one.  So the main term p0*p0 and the 2^-8-smaller cross terms
+// accumulate in two separate TMEM accumulators (the cross terms then truncate at 2^-8 of the scale and the main one
+// sees a third of the events) which the epilogue adds in fp32.
 //
 //   GATED : D[t, (a|b) c] = sum_{j,ci} Xd[b, t+off_j, ci] * W[j, (a|b) c, ci]    M = 128 time steps, N = 128 a | 128 b
 //   CONV  : D[t, n]       = sum_{j,kc} A[b, t+off_j, kc]  * W[j, n, kc]           M = 128 time steps, N = NBOX x 128
@@ -72,8 +74,18 @@ struct TcCfg {
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
     static constexpr int SMEM = STAGES * STAGE + 1024 + 512;
-    static constexpr int NCOLS = 128 * NBOX;
+    static constexpr int NCOLS = 128 * NBOX;         // columns per accumulator; two accumulators (main, cross)
+    static constexpr int TMEM_COLS = 2 * NCOLS;
 };
+
+// main + cross accumulator -> registers, summed in fp32 (round-to-nearest)
+__device__ __forceinline__ void tmem_ld_add(uint32_t taddr, int cross_off, float* v) {
+    float c[32];
+    tmem_ld_32x32(taddr, v);
+    tmem_ld_32x32(taddr + cross_off, c);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += c[i];
+}
 
 template <int MODE, int NBOX, int BK, int NPL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -115,7 +127,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<NCOLS>(tmem_ptr);
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -164,14 +176,9 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
                 const uint64_t adv = (uint64_t)(kk * 2);             // 16 bf16 = 32 bytes, in 16-byte units
-                umma_bf16(tmem_base, da[0] + adv, db[0] + adv, idesc, (it | kk) != 0);
-                umma_bf16(tmem_base, da[0] + adv, db[1] + adv, idesc, 1);
-                umma_bf16(tmem_base, da[1] + adv, db[0] + adv, idesc, 1);
-                if (NPL == 3) {
-                    umma_bf16(tmem_base, da[1] + adv, db[1] + adv, idesc, 1);
-                    umma_bf16(tmem_base, da[0] + adv, db[2] + adv, idesc, 1);
-                    umma_bf16(tmem_base, da[2] + adv, db[0] + adv, idesc, 1);
-                }
+                umma_bf16(tmem_base, da[0] + adv, db[0] + adv, idesc, (it | kk) != 0);          // main accumulator
+                umma_bf16(tmem_base + NCOLS, da[0] + adv, db[1] + adv, idesc, (it | kk) != 0);  // cross accumulator
+                umma_bf16(tmem_base + NCOLS, da[1] + adv, db[0] + adv, idesc, 1);
             }
             umma_commit(&empty[s]);                                  // frees the stage once these MMAs retire
         }
@@ -188,8 +195,8 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const bool tv = t < p.T;
             for (int c32 = 0; c32 < 128; c32 += 32) {
                 float va[32], vb[32];
-                tmem_ld_32x32(taddr + c32, va);
-                tmem_ld_32x32(taddr + 128 + c32, vb);
+                tmem_ld_add(taddr + c32, NCOLS, va);
+                tmem_ld_add(taddr + 128 + c32, NCOLS, vb);
                 if (!tv) continue;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -216,7 +223,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const DropCfg drop = make_drop(p.p_drop, p.seed_ptr, p.salt);
             for (int c32 = 0; c32 < NCOLS; c32 += 32) {
                 float v[32];
-                tmem_ld_32x32(taddr + c32, v);
+                tmem_ld_add(taddr + c32, NCOLS, v);
                 if (!tv) continue;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -237,7 +244,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const size_t ma = (size_t)(m % p.msplit) * p.s_m + (size_t)(m / p.msplit) * p.s_mh;
             for (int c32 = 0; c32 < NCOLS; c32 += 32) {
                 float v[32];
-                tmem_ld_32x32(taddr + c32, v);
+                tmem_ld_add(taddr + c32, NCOLS, v);
                 if (m >= p.Mw) continue;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -249,7 +256,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<NCOLS>(tmem_base);
+    if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -353,8 +360,8 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
                          const float* res, float* y, float* save_a, float* save_s, int B, int C, int T, int k,
                          int dilation, int causal, int mode, int residual, void* stream) {
     DV3_REQUIRE(dv3_tc_supported(B, C, T, k), "tc_convblock_fwd: unsupported shape B=%d C=%d T=%d k=%d", B, C, T, k);
-    DV3_REQUIRE(npl == 2 || npl == 3, "tc_convblock_fwd: npl must be 2 or 3");
-    const int bk = npl == 3 ? 32 : tc_bk();
+    DV3_REQUIRE(npl == 2, "tc_convblock_fwd: npl must be 2");
+    const int bk = tc_bk();
     TcMaps maps;
     for (int pl = 0; pl < npl; ++pl) {
         if (encode_tmap_bf16_3d(&maps.a[pl], plane(xd, pl, (long long)B * T * C), C, T, B, (uint64_t)C * 2,
@@ -369,7 +376,6 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
     p.gate_mode = mode; p.residual = residual;
     dim3 grid((T + 127) / 128, C / 128, B);
     cudaStream_t st = (cudaStream_t)stream;
-    if (npl == 3) return launch_tc<TC_GATED, 2, 32, 3>(maps, p, grid, st, "tc_convblock_fwd(x6)");
     if (bk == 64) return launch_tc<TC_GATED, 2, 64, 2>(maps, p, grid, st, "tc_convblock_fwd");
     return launch_tc<TC_GATED, 2, 32, 2>(maps, p, grid, st, "tc_convblock_fwd");
 }
@@ -383,8 +389,8 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
                 float alpha, void* stream) {
     DV3_REQUIRE(T % 8 == 0 && k >= 1 && k <= MAX_TAPS_TC && (k == 1 || Nc % 128 == 0) && B <= 65535,
                 "tc_conv: unsupported shape B=%d Kc=%d Nc=%d T=%d k=%d", B, Kc, Nc, T, k);
-    DV3_REQUIRE(npl == 2 || npl == 3, "tc_conv: npl must be 2 or 3");
-    const int bk = npl == 3 ? 32 : tc_bk();
+    DV3_REQUIRE(npl == 2, "tc_conv: npl must be 2");
+    const int bk = tc_bk();
     const int Kp = (Kc + 7) / 8 * 8;
     TcMaps maps;
     for (int pl = 0; pl < npl; ++pl) {
@@ -404,12 +410,10 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
     const bool wide = Nc > 128 && (long long)t_tiles * ((Nc + 255) / 256) * B >= 120;
     if (wide) {
         dim3 grid(t_tiles, (Nc + 255) / 256, B);
-        if (npl == 3) return launch_tc<TC_CONV, 2, 32, 3>(maps, p, grid, st, "tc_conv(x6)");
         if (bk == 64) return launch_tc<TC_CONV, 2, 64, 2>(maps, p, grid, st, "tc_conv");
         return launch_tc<TC_CONV, 2, 32, 2>(maps, p, grid, st, "tc_conv");
     }
     dim3 grid(t_tiles, (Nc + 127) / 128, B);
-    if (npl == 3) return launch_tc<TC_CONV, 1, 32, 3>(maps, p, grid, st, "tc_conv(x6)");
     if (bk == 64) return launch_tc<TC_CONV, 1, 64, 2>(maps, p, grid, st, "tc_conv");
     return launch_tc<TC_CONV, 1, 32, 2>(maps, p, grid, st, "tc_conv");
 }

@@ -15,11 +15,10 @@ MODE_GLU, MODE_HIGHWAY = 0, 1
 
 # Arithmetic of the ConvBlock contractions:
 #   "fp32"   exact-fp32 CUDA-core kernels (csrc/conv.cu)
-#   "tc"     tcgen05 tensor cores with split-bf16 operands (csrc/tc_gemm.cu): forward GEMMs with 3 planes / 6 products
-#            (fp32-equivalent, full-depth outputs stay inside rtol 1e-3 / atol 1e-4), backward GEMMs with 2 planes /
-#            3 products (~1e-5 per block).  Shapes the tensor-core kernels do not cover (C % 128 != 0, T % 8 != 0, tiny
-#            GEMMs) still run on the fp32 kernels.
-#   "bf16x3" as "tc" but 2 planes / 3 products in the forward too (fastest; ~1e-5 per block, ~2e-4 at full depth)
+#   "tc"     tcgen05 tensor cores with split-bf16 operands, hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM
+#            (csrc/tc_gemm.cu): every output / gradient of a block within ~1e-5 of the exact-fp32 kernels.  Shapes the
+#            tensor-core kernels do not cover (C % 128 != 0, T % 8 != 0, tiny GEMMs) still run on the fp32 kernels.
+#            ("bf16x3" is accepted as an alias.)
 conv_math = os.environ.get("DV3_CONV_MATH", "fp32")
 
 
@@ -181,8 +180,9 @@ class _ConvBlockFn(torch.autograd.Function):
 
 
 def _fwd_planes():
-    """Planes per operand in FORWARD GEMMs: 3 ("x6", fp32-equivalent) in strict "tc" mode, 2 ("x3") in "bf16x3"."""
-    return 3 if conv_math == "tc" else 2
+    """bf16 planes per operand (hi, lo).  A 3-plane / 6-product variant was measured to be LESS accurate: the tensor
+    core's truncating accumulation (one event per MMA) dominates the operand-split error (see csrc/tc_gemm.cu)."""
+    return 2
 
 
 def _pad8(n):

@@ -94,6 +94,51 @@ def training_loss(outs, batch, r=1, downsample_step=4, masked_loss_weight=0.5, b
     return loss
 
 
+class _FusedLossFn(torch.autograd.Function):
+    """All four training losses and their gradients in 3 kernel launches (csrc/loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, mel_out, lin_out, attn, done_hat, mel, y, done, target_lengths, input_lengths, r,
+                downsample_step, w, bw, sigma, use_attn):
+        dev = mel_out.device
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        mel_out, lin_out, attn, done_hat = [t.contiguous() for t in (mel_out, lin_out, attn, done_hat)]
+        loss = torch.zeros(1, device=dev)
+        g_mel, g_lin = torch.empty_like(mel_out), torch.empty_like(lin_out)
+        g_attn, g_done = torch.empty_like(attn), torch.empty_like(done_hat)
+        dec_len = (target_lengths // (r * downsample_step)).contiguous()
+        B, Td, Dm = mel_out.shape
+        lib.call("dv3_spec_loss", vp(mel_out), vp(mel.contiguous()), vp(dec_len), vp(g_mel), vp(loss), B, Td, Dm, r,
+                 float(w), float(bw), st)
+        _, Tl, Dl = lin_out.shape
+        lin_len = target_lengths.contiguous() if downsample_step > 1 else dec_len
+        lib.call("dv3_spec_loss", vp(lin_out), vp(y.contiguous()), vp(lin_len), vp(g_lin), vp(loss), B, Tl, Dl, r,
+                 float(w), float(bw), st)
+        A, _, _, Ts = attn.shape
+        dec_len_attn = (target_lengths // r // downsample_step).contiguous()
+        lib.call("dv3_aux_loss", vp(done_hat), vp(done.contiguous()), vp(g_done), done_hat.numel(), vp(attn),
+                 vp(g_attn), vp(input_lengths.contiguous()), vp(dec_len_attn), A, B, attn.shape[2], Ts, float(sigma),
+                 int(use_attn), vp(loss), st)
+        ctx.save_for_backward(g_mel, g_lin, g_attn, g_done)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        g_mel, g_lin, g_attn, g_done = ctx.saved_tensors
+        return (g_mel * gout, g_lin * gout, g_attn * gout, g_done * gout) + (None,) * 11
+
+
+def fused_training_loss(outs, batch, r=1, downsample_step=4, masked_loss_weight=0.5, binary_divergence_weight=0.1,
+                        guided_attention_sigma=0.2, use_guided_attention=True):
+    """Same value and gradients as ``training_loss`` (reference train.py:665-740), computed by csrc/loss.cu."""
+    mel_out, lin_out, attn, done_hat = outs
+    return _FusedLossFn.apply(mel_out, lin_out, attn, done_hat, batch["mel"], batch["y"], batch["done"],
+                              batch["target_lengths"], batch["input_lengths_dev"], r, downsample_step,
+                              masked_loss_weight, binary_divergence_weight, guided_attention_sigma,
+                              use_guided_attention)
+
+
 class ParameterArena:
     """Re-homes the trainable parameters of ``model`` into one flat fp32 buffer (and their gradients into
     another).  ``state_dict`` / ``load_state_dict`` keep working: parameters stay nn.Parameters, only their
@@ -177,7 +222,8 @@ class TrainStep:
 
     def __init__(self, model, init_lr=5e-4, betas=(0.5, 0.9), eps=1e-6, clip_thresh=0.1, r=1, downsample_step=4,
                  masked_loss_weight=0.5, binary_divergence_weight=0.1, guided_attention_sigma=0.2,
-                 use_guided_attention=True, lr_schedule=noam_learning_rate_decay, use_graph=False):
+                 use_guided_attention=True, lr_schedule=noam_learning_rate_decay, use_graph=False,
+                 fused_loss=True):
         self.model = model
         self.arena = ParameterArena(model)
         self.opt = FlatAdam(self.arena, init_lr, betas, eps, clip_thresh)
@@ -186,6 +232,7 @@ class TrainStep:
                             binary_divergence_weight=binary_divergence_weight,
                             guided_attention_sigma=guided_attention_sigma,
                             use_guided_attention=use_guided_attention)
+        self.loss_fn = fused_training_loss if fused_loss else training_loss
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.global_step = 0
         self.use_graph = use_graph
@@ -200,7 +247,7 @@ class TrainStep:
         outs = self.model(batch["x"], batch["mel"], speaker_ids=batch.get("speaker_ids"),
                           text_positions=batch["text_positions"], frame_positions=batch["frame_positions"],
                           input_lengths=batch["input_lengths_dev"])
-        loss = training_loss(outs, batch, **self.loss_kw)
+        loss = self.loss_fn(outs, batch, **self.loss_kw)
         loss.backward()
         return loss.detach()
 

@@ -182,6 +182,17 @@ int dv3_tc_wgrad_nsplit(int B, int Mw, int Nw, int T, int k);
 int dv3_tc_wgrad(const void* dy, const void* xs, float* dw_partials, long long split_stride, int B, int Mw, int Nw,
                  int T, int k, int msplit, long long s_m, long long s_mh, long long s_n, long long s_j, void* stream);
 
+/* ---- fused training losses + gradients: reference train.py:537-601 (spec_loss, guided_attention) and :704-740.
+ * dv3_spec_loss: pairs (y_hat[b,t], y[b,t+r]), t < T-r; lengths int64 [B] valid target frames; adds
+ * (1-bw)*L1 + bw*binary_divergence (each = w*masked_mean + (1-w)*mean) to loss[0]; grad (B,T,D) = dLoss/dy_hat.
+ * dv3_aux_loss: adds BCE(done_hat, done) and, if use_attn, mean(attn*W) with the guided-attention mask
+ * W[b,t,n] = 1-exp(-(n/in_len[b] - t/dec_len[b])^2/(2 sigma^2)) built on the fly; writes both gradients. */
+int dv3_spec_loss(const float* y_hat, const float* y, const long long* lengths, float* grad, float* loss, int B,
+                  int T, int D, int r, float masked_loss_weight, float binary_divergence_weight, void* stream);
+int dv3_aux_loss(const float* done_hat, const float* done, float* d_done, long long n_done, const float* attn,
+                 float* d_attn, const long long* in_len, const long long* dec_len, int A, int B, int Td, int Ts,
+                 float sigma, int use_attn, float* loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,17 @@ def test_training_loss_matches_oracle_and_step_runs():
     dev = to_device(host, "cuda")
     got = training_loss(tuple(o.cuda() for o in outs), dev)
     torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-6)
+    # fused loss kernels: same value, same gradients as the torch-op restatement
+    from deepvoice3_pytorch_b200.train_step import fused_training_loss
+    leaves = [o.cuda().requires_grad_(True) for o in outs]
+    training_loss(tuple(leaves), dev).backward()
+    want_g = [t.grad.clone() for t in leaves]
+    leaves2 = [o.cuda().requires_grad_(True) for o in outs]
+    got2 = fused_training_loss(tuple(leaves2), dev)
+    torch.testing.assert_close(got2.cpu(), want, rtol=1e-5, atol=1e-6)
+    got2.backward()
+    for a_, b_ in zip(leaves2, want_g):
+        torch.testing.assert_close(a_.grad, b_, rtol=2e-4, atol=1e-9)
     W = guided_attention_mask(dev["input_lengths_dev"], dev["target_lengths"] // 4, 16, 20, 0.2)
     np.testing.assert_allclose(W.cpu().numpy(), O.guided_attentions(host["input_lengths"], np.array([16, 12, 8]),
                                                                    16, 20, 0.2), rtol=1e-6, atol=1e-7)
