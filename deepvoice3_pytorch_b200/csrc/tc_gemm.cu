@@ -31,7 +31,7 @@ constexpr int SMEM_LIMIT = 232448;          // 227 KB opt-in dynamic shared memo
 
 enum { TC_GATED = 0, TC_CONV = 1, TC_WGRAD = 2 };
 
-struct TcMaps { CUtensorMap a[3]; CUtensorMap b[3]; };
+struct TcMaps { CUtensorMap a[2]; CUtensorMap b[2]; CUtensorMap bs[2]; };   // bs: B boxes of 128/CL rows (multicast slices)
 
 struct TcParams {
     int T, B;
@@ -87,7 +87,10 @@ __device__ __forceinline__ void tmem_ld_add(uint32_t taddr, int cross_off, float
     for (int i = 0; i < 32; ++i) v[i] += c[i];
 }
 
-template <int MODE, int NBOX, int BK, int NPL>
+// CL > 1: thread-block cluster of CL CTAs along the batch axis.  They need the same weight tiles, so CTA r fetches
+// rows [r*128/CL, (r+1)*128/CL) of every weight box and TMA-multicasts them into all CL shared memories: weight
+// bytes read from L2 per CTA drop by CL (the kernels are L2->SMEM bandwidth bound, ~3.8 TB/s measured).
+template <int MODE, int NBOX, int BK, int NPL, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<NBOX, BK, NPL>;
@@ -120,16 +123,24 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         n_iters = (b_end > b_beg ? b_end - b_beg : 0) * p.kb_n;
     }
 
+    static_assert(CL == 1 || MODE != TC_WGRAD, "weight-gradient tiles share no operand across the batch");
+    constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1);
+    constexpr int SLICE_ROWS = 128 / CL, SLICE_BYTES = SLICE_ROWS * BK * 2;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) { prefetch_tmap(&maps.a[i]); prefetch_tmap(&maps.b[i]); }
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < NPL; ++i) { prefetch_tmap(&maps.a[i]); prefetch_tmap(CL > 1 ? &maps.bs[i] : &maps.b[i]); }
+        // empty[s] collects one tcgen05.commit arrival from every CTA of the cluster (all of them read the slices
+        // this CTA multicasts); full[s] gets this CTA's expect_tx arrival + bytes from all CL producers
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // every CTA's barriers are initialised before any remote arrival
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -155,8 +166,17 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
             for (int pl = 0; pl < NPL; ++pl) {
                 tma_load_3d(st + pl * TILE, &maps.a[pl], &full[s], ax, ay, az);
-                tma_load_3d(st + (NPL + pl * NBOX) * TILE, &maps.b[pl], &full[s], bx, by0, bz);
-                if (NBOX == 2) tma_load_3d(st + (NPL + pl * NBOX + 1) * TILE, &maps.b[pl], &full[s], bx, by1, bz);
+                if (CL == 1) {
+                    tma_load_3d(st + (NPL + pl * NBOX) * TILE, &maps.b[pl], &full[s], bx, by0, bz);
+                    if (NBOX == 2) tma_load_3d(st + (NPL + pl * NBOX + 1) * TILE, &maps.b[pl], &full[s], bx, by1, bz);
+                } else {
+                    const int ro = crank * SLICE_ROWS, so = crank * SLICE_BYTES;
+                    tma_load_3d_multicast(st + (NPL + pl * NBOX) * TILE + so, &maps.bs[pl], &full[s], bx, by0 + ro, bz,
+                                          CL_MASK);
+                    if (NBOX == 2)
+                        tma_load_3d_multicast(st + (NPL + pl * NBOX + 1) * TILE + so, &maps.bs[pl], &full[s], bx,
+                                              by1 + ro, bz, CL_MASK);
+                }
             }
         }
     } else if (warp == 1 && lane == 0) {
@@ -180,7 +200,8 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 umma_bf16(tmem_base + NCOLS, da[0] + adv, db[1] + adv, idesc, (it | kk) != 0);  // cross accumulator
                 umma_bf16(tmem_base + NCOLS, da[1] + adv, db[0] + adv, idesc, 1);
             }
-            umma_commit(&empty[s]);                                  // frees the stage once these MMAs retire
+            if (CL == 1) umma_commit(&empty[s]);                     // frees the stage once these MMAs retire
+            else umma_commit_multicast(&empty[s], CL_MASK);          // ... in every CTA that multicasts into it
         }
         umma_commit(tmem_full);
     } else if (warp >= 2) {
@@ -190,52 +211,83 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int q = warp & 3;                                      // TMEM lane quarter this warp may touch
         const int row = q * 32 + lane;                               // accumulator row (M index)
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        // NOTE on the epilogue loads: residual / addend / bias reads go through __ldg (ld.global.nc) and are issued
+        // as a batch of 32 independent loads BEFORE the dependent math and stores of the chunk.  With plain loads the
+        // compiler must order every load after the previous iteration's stores (possible aliasing), which serialised
+        // 128 global-memory round trips per thread and made the epilogue as long as the whole K loop (ncu: 40 % of
+        // the stall samples sat on the first use of these loads).
         if (MODE == TC_GATED) {
             const int t = a_row0 + row, b = a_z, C = p.Nc;
             const bool tv = t < p.T;
+            const float* __restrict__ bias = p.bias;
+            const float* __restrict__ res = p.res;
+            const float* __restrict__ spk = p.spk;
+            float* __restrict__ yo = p.y;
+            float* __restrict__ ao = p.save_a;
+            float* __restrict__ so = p.save_s;
+            const bool need_res = (p.gate_mode != 0) || p.residual;
+            const size_t base = ((size_t)b * C + b_row0) * p.T + (tv ? t : 0);
             for (int c32 = 0; c32 < 128; c32 += 32) {
-                float va[32], vb[32];
+                float va[32], vb[32], rr[32];
                 tmem_ld_add(taddr + c32, NCOLS, va);
                 tmem_ld_add(taddr + 128 + c32, NCOLS, vb);
                 if (!tv) continue;
+                const size_t cb = base + (size_t)c32 * p.T;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) rr[i] = need_res ? __ldg(&res[cb + (size_t)i * p.T]) : 0.f;
+                if (spk) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) va[i] += __ldg(&spk[cb + (size_t)i * p.T]);
+                }
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const int c = b_row0 + c32 + i;
-                    const size_t idx = ((size_t)b * C + c) * p.T + t;
-                    float a = va[i] + p.bias[c];
-                    if (p.spk) a += p.spk[idx];
-                    const float s = sigmoidf_(vb[i] + p.bias[C + c]);
+                    const size_t idx = cb + (size_t)i * p.T;
+                    const float a = va[i] + __ldg(&bias[c]);
+                    const float s = sigmoidf_(vb[i] + __ldg(&bias[C + c]));
                     float y;
                     if (p.gate_mode == 0) {
                         y = a * s;
-                        if (p.residual) y = (y + p.res[idx]) * 0.70710678118654752f;
+                        if (p.residual) y = (y + rr[i]) * 0.70710678118654752f;
                     } else {
-                        y = s * a + (1.f - s) * p.res[idx];
+                        y = s * a + (1.f - s) * rr[i];
                     }
-                    p.y[idx] = y;
-                    if (p.save_a) p.save_a[idx] = a;
-                    if (p.save_s) p.save_s[idx] = s;
+                    yo[idx] = y;
+                    if (ao) ao[idx] = a;
+                    if (so) so[idx] = s;
                 }
             }
         } else if (MODE == TC_CONV) {
             const int t = a_row0 + row, b = a_z;
             const bool tv = t < p.T;
             const DropCfg drop = make_drop(p.p_drop, p.seed_ptr, p.salt);
+            const float* __restrict__ bias = p.bias;
+            const float* __restrict__ e1 = p.e1;
+            const float* __restrict__ e2 = p.e2;
+            float* __restrict__ out = p.out;
             for (int c32 = 0; c32 < NCOLS; c32 += 32) {
-                float v[32];
+                float v[32], x1[32], x2[32];
                 tmem_ld_add(taddr + c32, NCOLS, v);
                 if (!tv) continue;
+                const int n0 = b_row0 + c32;
+                const size_t cb = ((size_t)b * p.Nc + n0) * p.T + t;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const int n = b_row0 + c32 + i;
+                    const bool ok = n0 + i < p.Nc;
+                    x1[i] = (p.addmode != 0 && ok) ? __ldg(&e1[cb + (size_t)i * p.T]) : 0.f;
+                    x2[i] = (p.addmode == 2 && ok) ? __ldg(&e2[cb + (size_t)i * p.T]) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int n = n0 + i;
                     if (n >= p.Nc) continue;
-                    const size_t idx = ((size_t)b * p.Nc + n) * p.T + t;
+                    const size_t idx = cb + (size_t)i * p.T;
                     float g = v[i] * drop_scale(drop, (uint32_t)idx);
-                    if (p.bias) g += p.bias[n];
-                    if (p.addmode == 1) g += p.alpha * p.e1[idx];
-                    else if (p.addmode == 2) g += p.e1[idx] * (1.f - p.e2[idx]);
+                    if (bias) g += __ldg(&bias[n]);
+                    if (p.addmode == 1) g += p.alpha * x1[i];
+                    else if (p.addmode == 2) g += x1[i] * (1.f - x2[i]);
                     if (p.relu) g = fmaxf(g, 0.f);
-                    p.out[idx] = g;
+                    out[idx] = g;
                 }
             }
         } else {
@@ -256,6 +308,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // no CTA may exit while peers still multicast into / signal it
     if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
@@ -297,22 +350,48 @@ int encode_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_
     return 0;
 }
 
-template <int MODE, int NBOX, int BK, int NPL>
+template <int MODE, int NBOX, int BK, int NPL, int CL = 1>
 static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStream_t st, const char* what) {
     using Cfg = TcCfg<NBOX, BK, NPL>;
     static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
     static bool configured = false;
+    auto kern = tc_conv_kernel<MODE, NBOX, BK, NPL, CL>;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<MODE, NBOX, BK, NPL>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) {
             set_error("%s: cannot set %d B dynamic smem: %s", what, Cfg::SMEM, cudaGetErrorString(e));
             return 1;
         }
         configured = true;
     }
-    tc_conv_kernel<MODE, NBOX, BK, NPL><<<grid, TC_THREADS, Cfg::SMEM, st>>>(maps, p);
+    if (CL == 1) {
+        kern<<<grid, TC_THREADS, Cfg::SMEM, st>>>(maps, p);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = CL;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, p);
+        if (e != cudaSuccess) { set_error("%s: cluster launch failed: %s", what, cudaGetErrorString(e)); return 1; }
+    }
     return check_launch(what);
+}
+
+static int g_cl = 0;
+static int tc_cluster() {                  // weight-multicast cluster size along the batch axis: DV3_TC_CLUSTER=1|2|4
+    if (!g_cl) {
+        const char* e = getenv("DV3_TC_CLUSTER");
+        const int v = e ? atoi(e) : 1;
+        g_cl = (v == 2 || v == 4) ? v : 1;
+    }
+    return g_cl;
+}
+static int pick_cluster(int B) {
+    int cl = tc_cluster();
+    while (cl > 1 && B % cl != 0) cl >>= 1;
+    return cl;
 }
 
 static int g_bk = 0;
@@ -363,11 +442,15 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
     DV3_REQUIRE(npl == 2, "tc_convblock_fwd: npl must be 2");
     const int bk = tc_bk();
     TcMaps maps;
+    const int cl = pick_cluster(B);
     for (int pl = 0; pl < npl; ++pl) {
         if (encode_tmap_bf16_3d(&maps.a[pl], plane(xd, pl, (long long)B * T * C), C, T, B, (uint64_t)C * 2,
                                 (uint64_t)T * C * 2, bk, 128)) return 1;
         if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
                                 (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 128)) return 1;
+        if (cl > 1 && encode_tmap_bf16_3d(&maps.bs[pl], plane(w, pl, (long long)k * 2 * C * C), C,
+                                          (uint64_t)k * 2 * C, 1, (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk,
+                                          128 / cl)) return 1;
     }
     TcParams p = {};
     p.T = T; p.B = B; p.Kc = C; p.Nc = C; p.rows_per_tap = 2 * C; p.k = k; p.kb_n = (C + bk - 1) / bk;
@@ -377,6 +460,8 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
     dim3 grid((T + 127) / 128, C / 128, B);
     cudaStream_t st = (cudaStream_t)stream;
     if (bk == 64) return launch_tc<TC_GATED, 2, 64, 2>(maps, p, grid, st, "tc_convblock_fwd");
+    if (cl == 4) return launch_tc<TC_GATED, 2, 32, 2, 4>(maps, p, grid, st, "tc_convblock_fwd(cluster4)");
+    if (cl == 2) return launch_tc<TC_GATED, 2, 32, 2, 2>(maps, p, grid, st, "tc_convblock_fwd(cluster2)");
     return launch_tc<TC_GATED, 2, 32, 2>(maps, p, grid, st, "tc_convblock_fwd");
 }
 
@@ -393,11 +478,14 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
     const int bk = tc_bk();
     const int Kp = (Kc + 7) / 8 * 8;
     TcMaps maps;
+    const int cl = pick_cluster(B);
     for (int pl = 0; pl < npl; ++pl) {
         if (encode_tmap_bf16_3d(&maps.a[pl], plane(a, pl, (long long)B * T * Kp), Kc, T, B, (uint64_t)Kp * 2,
                                 (uint64_t)T * Kp * 2, bk, 128)) return 1;
         if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
                                 (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, 128)) return 1;
+        if (cl > 1 && encode_tmap_bf16_3d(&maps.bs[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
+                                          (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, 128 / cl)) return 1;
     }
     TcParams p = {};
     p.T = T; p.B = B; p.Kc = Kc; p.Nc = Nc; p.rows_per_tap = Nc; p.k = k; p.kb_n = (Kc + bk - 1) / bk;
@@ -411,10 +499,14 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
     if (wide) {
         dim3 grid(t_tiles, (Nc + 255) / 256, B);
         if (bk == 64) return launch_tc<TC_CONV, 2, 64, 2>(maps, p, grid, st, "tc_conv");
+        if (cl == 4) return launch_tc<TC_CONV, 2, 32, 2, 4>(maps, p, grid, st, "tc_conv(cluster4)");
+        if (cl == 2) return launch_tc<TC_CONV, 2, 32, 2, 2>(maps, p, grid, st, "tc_conv(cluster2)");
         return launch_tc<TC_CONV, 2, 32, 2>(maps, p, grid, st, "tc_conv");
     }
     dim3 grid(t_tiles, (Nc + 127) / 128, B);
     if (bk == 64) return launch_tc<TC_CONV, 1, 64, 2>(maps, p, grid, st, "tc_conv");
+    if (cl == 4) return launch_tc<TC_CONV, 1, 32, 2, 4>(maps, p, grid, st, "tc_conv(cluster4)");
+    if (cl == 2) return launch_tc<TC_CONV, 1, 32, 2, 2>(maps, p, grid, st, "tc_conv(cluster2)");
     return launch_tc<TC_CONV, 1, 32, 2>(maps, p, grid, st, "tc_conv");
 }
 

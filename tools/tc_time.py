@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Time the three tensor-core kernels of the big ConvBlock shapes in isolation (CUDA events, no L2 flush)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from deepvoice3_pytorch_b200 import ops  # noqa: E402
+
+ops.conv_math = "tc"
+dev = "cuda"
+for (B, C, T, k, d) in [(16, 512, 800, 3, 1), (16, 256, 800, 3, 3), (16, 512, 128, 3, 9), (16, 256, 200, 3, 9)]:
+    v = (torch.randn(2 * C, C, k, device=dev) * (4.0 / (k * C)) ** 0.5).requires_grad_(True)
+    g = v.detach().pow(2).sum((1, 2), keepdim=True).sqrt().requires_grad_(True)
+    bias = torch.zeros(2 * C, device=dev, requires_grad=True)
+    x = torch.randn(B, C, T, device=dev, requires_grad=True)
+    dy = torch.randn(B, C, T, device=dev)
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        for _ in range(5):
+            y = ops.convblock(x, v, g, bias, None, k, d, False, ops.MODE_GLU, True)
+            y.backward(dy)
+        torch.cuda.synchronize()
+    rows = {}
+    for e in prof.key_averages():
+        if "tc_conv_kernel" in e.key:
+            rows[e.key.split("tc_conv_kernel")[1][:14]] = e.device_time_total / e.count
+    flops = 2.0 * B * T * 2 * C * C * k
+    print("B=%d C=%d T=%d: " % (B, C, T) + "  ".join("%s %.1f us (%.0f TF)" % (kk, vv, flops / vv / 1e6)
+                                                      for kk, vv in sorted(rows.items())), flush=True)
