@@ -292,16 +292,29 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             }
         } else {
             const int m = a_row0 + row;
-            float* out = p.dw + (size_t)wg_split * p.split_stride + (size_t)wg_j * p.s_j;
+            float* __restrict__ out = p.dw + (size_t)wg_split * p.split_stride + (size_t)wg_j * p.s_j;
             const size_t ma = (size_t)(m % p.msplit) * p.s_m + (size_t)(m / p.msplit) * p.s_mh;
+            // partials with unit stride along n ([split][j][m][n]): each thread owns a contiguous run -> float4
+            // stores, every 32-byte sector written whole (the v-layout (m, n, j) scatters 4-byte stores k apart)
+            const bool vec = (p.s_n == 1) && ((p.Nc & 3) == 0) && (((ma + (size_t)wg_j * p.s_j +
+                                                                     (size_t)wg_split * p.split_stride) & 3) == 0);
             for (int c32 = 0; c32 < NCOLS; c32 += 32) {
                 float v[32];
                 tmem_ld_add(taddr + c32, NCOLS, v);
                 if (m >= p.Mw) continue;
+                const int n0 = b_row0 + c32;
+                if (n_iters == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int n = b_row0 + c32 + i;
-                    if (n < p.Nc) out[ma + (size_t)n * p.s_n] = (n_iters > 0) ? v[i] : 0.f;
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                }
+                if (vec && n0 + 32 <= p.Nc) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4*>(&out[ma + n0 + i]) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (n0 + i < p.Nc) out[ma + (size_t)(n0 + i) * p.s_n] = v[i];
                 }
             }
         }

@@ -58,8 +58,11 @@ __global__ void wn_pack_kernel(const float* __restrict__ v, const float* __restr
 // backward, one CTA (256 threads) per row:  dW = sum_s partial[s] ;  dot = <dW, v>
 //   dg = dot * inv_norm ;  dv = scale*dW - scale*dot*inv_norm^2 * v
 // (one warp per row left the big layers -- 1024 rows x 1536 x up to 16 partials -- at 0.4 TB/s.)
+// Partials are either in v's own layout (jmajor_X == 0: element e of row r at r*L + e) or tap-major
+// (jmajor_X = X > 0: element (r, x, j) at (j*R + r)*X + x -- what the tensor-core weight-gradient kernel writes with
+// contiguous float4 stores).
 __global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ dw_partials, long long split_stride,
-                                                     int nsplit, const float* __restrict__ v,
+                                                     int nsplit, int jmajor_X, const float* __restrict__ v,
                                                      const float* __restrict__ g,
                                                      const float* __restrict__ inv_norm, float* __restrict__ dv,
                                                      float* __restrict__ dg, int R, int L) {
@@ -68,8 +71,18 @@ __global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ d
     const int r = blockIdx.x, tid = threadIdx.x;
     const size_t base = (size_t)r * L;
     float dot = 0.f;
-    const bool vec = ((L & 3) == 0) && ((split_stride & 3) == 0);
-    if (vec) {
+    const bool vec = ((L & 3) == 0) && ((split_stride & 3) == 0) && jmajor_X == 0;
+    if (jmajor_X > 0) {
+        const int X = jmajor_X, k = L / X;
+        for (int q = tid; q < L; q += 256) {             // q = j*X + x: coalesced over the partials
+            const int j = q / X, x = q - j * X, e = x * k + j;
+            const size_t po = ((size_t)j * R + r) * X + x;
+            float d = 0.f;
+            for (int s = 0; s < nsplit; ++s) d += dw_partials[(size_t)s * split_stride + po];
+            dv[base + e] = d;
+            dot = fmaf(d, v[base + e], dot);
+        }
+    } else if (vec) {
         const int L4 = L >> 2;
         for (int e = tid; e < L4; e += 256) {
             float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -101,7 +114,13 @@ __global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ d
     dot = s_dot;
     const float inv = inv_norm[r], sc = g[r] * inv, c2 = sc * dot * inv * inv;
     // each thread rewrites exactly the elements it stored above
-    if (vec) {
+    if (jmajor_X > 0) {
+        const int X = jmajor_X, k = L / X;
+        for (int q = tid; q < L; q += 256) {             // same thread -> same elements as in the first pass
+            const int j = q / X, x = q - j * X, e = x * k + j;
+            dv[base + e] = sc * dv[base + e] - c2 * v[base + e];
+        }
+    } else if (vec) {
         const int L4 = L >> 2;
         for (int e = tid; e < L4; e += 256) {
             float4 d = *reinterpret_cast<float4*>(&dv[base + 4 * e]);
@@ -135,12 +154,12 @@ int dv3_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* s
     return check_launch("weightnorm_fwd(pack)");
 }
 
-// dw_partials: [nsplit][R*X*k] in v's own layout.
-int dv3_weightnorm_bwd(const float* dw_partials, long long split_stride, int nsplit, const float* v,
-                       const float* g, const float* inv_norm, float* dv, float* dg, int R, int X, int k,
-                       void* stream) {
+// dw_partials: [nsplit][R*X*k]; tap_major = 0: v's own layout (r, x, j); 1: [j][r][x].
+int dv3_weightnorm_bwd(const float* dw_partials, long long split_stride, int nsplit, int tap_major,
+                       const float* v, const float* g, const float* inv_norm, float* dv, float* dg, int R, int X,
+                       int k, void* stream) {
     wn_bwd_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(
-        dw_partials, split_stride, nsplit, v, g, inv_norm, dv, dg, R, X * k);
+        dw_partials, split_stride, nsplit, tap_major ? X : 0, v, g, inv_norm, dv, dg, R, X * k);
     return check_launch("weightnorm_bwd");
 }
 

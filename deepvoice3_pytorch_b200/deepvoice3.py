@@ -213,12 +213,15 @@ class Decoder(nn.Module):
 
         alignments = []
         for f, attention in zip(self.convolutions, self.attention):
+            if attention is None:
+                # x = (f(x) + x) * sqrt(.5): the block kernel's own residual epilogue
+                x = f(x, speaker_embed_btc, fuse_residual=True)
+                continue
             residual = x
             x = f(x, speaker_embed_btc)
-            if attention is not None:
-                q = x if frame_pos_bct is None else x + frame_pos_bct
-                x, alignment = attention.forward_bct(q, keys_bct, values_bct, mask)
-                alignments.append(alignment)
+            q = x if frame_pos_bct is None else x + frame_pos_bct
+            x, alignment = attention.forward_bct(q, keys_bct, values_bct, mask)
+            alignments.append(alignment)
             x = (x + residual) * SQRT_HALF
 
         decoder_states = ops.transpose12(x)

@@ -131,14 +131,18 @@ class Conv1dGLU(_GatedConv):
         self._make_conv(in_channels, out_channels, kernel_size, padding, dilation, causal, dropout, std_mul)
         self.speaker_proj = Linear(speaker_embed_dim, out_channels) if n_speakers > 1 else None
 
-    def forward(self, x, speaker_embed=None):
-        """x (B, C, T); speaker_embed (B, T, S) time-expanded (and, in training, dropped-out) embedding."""
+    def forward(self, x, speaker_embed=None, fuse_residual=None):
+        """x (B, C, T); speaker_embed (B, T, S) time-expanded (and, in training, dropped-out) embedding.
+        fuse_residual=True computes (block(x) + x)*sqrt(.5) in the kernel even when the module was built with
+        residual=False -- the decoder applies exactly that outside the block when no attention layer sits in between
+        (reference deepvoice3.py:333-349)."""
         spk = None
         if self.speaker_proj is not None:
             spk = F.softsign(self.speaker_proj.forward_bct(ops.transpose12(speaker_embed)))
         c = self.conv
+        residual = self.residual if fuse_residual is None else bool(fuse_residual)
         return ops.convblock(x, c.weight_v, c.weight_g, c.bias, spk, c.kernel_size[0], c.dilation[0],
-                             self.causal, ops.MODE_GLU, self.residual, self.dropout, self.training)
+                             self.causal, ops.MODE_GLU, residual, self.dropout, self.training)
 
 
 class HighwayConv1d(_GatedConv):

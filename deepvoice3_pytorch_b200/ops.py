@@ -107,13 +107,19 @@ def _wn_conv_fwd(v, g):
     return w_f, w_b, inv
 
 
-def _wn_bwd(partials, nsplit, v, g, inv):
+def _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=0):
+    """tap_major_k = 0: partials in v's layout; = k (> 0): partials as [j][R][X] (tensor-core weight gradient)."""
     dv = torch.empty_like(v)
     dg = torch.empty_like(g)
     R = v.shape[0]
-    X = v.numel() // R
-    lib.call("dv3_weightnorm_bwd", _p(partials), v.numel(), nsplit, _p(v), _p(g), _p(inv), _p(dv),
-             _p(dg), R, X, 1, _stream())
+    if tap_major_k:
+        X = v.numel() // R // tap_major_k
+        lib.call("dv3_weightnorm_bwd", _p(partials), v.numel(), nsplit, 1, _p(v), _p(g), _p(inv), _p(dv), _p(dg), R, X,
+                 tap_major_k, _stream())
+    else:
+        X = v.numel() // R
+        lib.call("dv3_weightnorm_bwd", _p(partials), v.numel(), nsplit, 0, _p(v), _p(g), _p(inv), _p(dv), _p(dg), R, X,
+                 1, _stream())
     return dv, dg
 
 
@@ -248,9 +254,10 @@ class _ConvBlockTCFn(torch.autograd.Function):
             nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, 2 * C, C, T, k)
             numel = v.numel()
             partials = torch.empty(nsplit, numel, device=dev)
-            lib.call("dv3_tc_wgrad", _p(d_bct), _p(x_bct), _p(partials), numel, B, 2 * C, C, T, k, 2 * C, C * k, 0,
-                     k, 1, _stream())
-            dv, dg = _wn_bwd(partials, nsplit, v, g, inv)
+            # partials [split][j][2C][C]: contiguous float4 stores from the GEMM epilogue
+            lib.call("dv3_tc_wgrad", _p(d_bct), _p(x_bct), _p(partials), numel, B, 2 * C, C, T, k, 2 * C, C, 0, 1,
+                     2 * C * C, _stream())
+            dv, dg = _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k)
         dspk = None
         if has_spk and ctx.needs_input_grad[4]:
             dspk = d_bct[0, :, :C, :].float() + d_bct[1, :, :C, :].float()
@@ -311,9 +318,9 @@ class _Conv1dTCFn(torch.autograd.Function):
             nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, Cout, Cin, T, k)
             numel = v.numel()
             partials = torch.empty(nsplit, numel, device=dev)
-            lib.call("dv3_tc_wgrad", _p(g_bct), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, Cout, Cin * k, 0, k,
-                     1, _stream())
-            dv, dg = _wn_bwd(partials, nsplit, v, g, inv)
+            lib.call("dv3_tc_wgrad", _p(g_bct), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, Cout, Cin, 0, 1,
+                     Cout * Cin, _stream())
+            dv, dg = _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k)
         return dx, dv, dg, dbias, None, None, None, None
 
 
