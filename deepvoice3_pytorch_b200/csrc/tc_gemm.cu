@@ -326,6 +326,143 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 }
 
 // ------------------------------------------------------------------------------------------------
+// Weight gradient straight from the (B,T,C) planes the forward / data-gradient GEMMs already use:
+//     D[m, n] (tap j) = sum_{b,t} dY[b, t, m] * Xd[b, t + off_j, n]
+// Both operands are "MN-major" here (channels contiguous, the contraction index t is the row): 64-channel x 32-row
+// TMA boxes (128-byte rows, SWIZZLE_128B), UMMA descriptors with the MN-major canonical layout
+// ((64 channels contiguous, chunk stride LBO), (8 rows x 128 B, group stride SBO)) and a_major = b_major = 1 in the
+// instruction descriptor.  The tap shift is a ROW coordinate of the TMA box (any alignment, out-of-bounds rows are
+// zero = the conv padding), so no time-shifted copies of the input are needed.
+// ------------------------------------------------------------------------------------------------
+struct TcMnParams {
+    int T, B, Mw, Nw, k;
+    int tap_off[MAX_TAPS_TC];
+    int nsplit, batches_per_split, kb_n;      // kb_n = 32-row time chunks per utterance
+    uint32_t lbo, sbo;                        // descriptor strides in bytes (chunk stride, 8-row group stride)
+    float* dw; long long split_stride;
+    int msplit; long long s_m, s_mh, s_n, s_j;
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+
+template <int NBOX>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_wgrad_mn_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcMnParams p) {
+    constexpr int BOX = 64 * 32 * 2;                     // 64 channels x 32 time steps of bf16 = 4 KB
+    constexpr int A_PL = 2 * BOX, B_PL = 2 * NBOX * BOX; // per plane: 128 rows of M, 128*NBOX columns of N
+    constexpr int STAGE = 2 * (A_PL + B_PL);
+    constexpr int STAGES = ((SMEM_LIMIT - 2048) / STAGE) > 6 ? 6 : ((SMEM_LIMIT - 2048) / STAGE);
+    constexpr int NCOLS = 128 * NBOX;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int wg_j = blockIdx.z % p.k, wg_split = blockIdx.z / p.k;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128 * NBOX;
+    const int b_beg = wg_split * p.batches_per_split;
+    int b_end = b_beg + p.batches_per_split; if (b_end > p.B) b_end = p.B;
+    const int n_iters = (b_end > b_beg ? b_end - b_beg : 0) * p.kb_n;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.a[1]); prefetch_tmap(&maps.b[0]); prefetch_tmap(&maps.b[1]);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<2 * NCOLS>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0 && lane == 0) {
+        for (int it = 0; it < n_iters; ++it) {
+            const int s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* st = smem + s * STAGE;
+            const int bi = it / p.kb_n, tc_ = it - bi * p.kb_n;
+            const int b = b_beg + bi, t0 = tc_ * 32;
+            mbar_arrive_expect_tx(&full[s], STAGE);
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    tma_load_3d(st + pl * A_PL + h * BOX, &maps.a[pl], &full[s], m0 + h * 64, t0, b);
+#pragma unroll
+                for (int q = 0; q < 2 * NBOX; ++q)
+                    tma_load_3d(st + 2 * A_PL + pl * B_PL + q * BOX, &maps.b[pl], &full[s], n0 + q * 64,
+                                t0 + p.tap_off[wg_j], b);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, NCOLS) | (1u << 15) | (1u << 16);   // A and B MN-major
+        for (int it = 0; it < n_iters; ++it) {
+            const int s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * STAGE);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {                        // 2 x UMMA_K(16 rows of 128 B)
+                const uint32_t ko = kk * 16 * 128;
+                const uint64_t a0 = make_desc_mn(sa + ko, p.lbo, p.sbo);
+                const uint64_t a1 = make_desc_mn(sa + A_PL + ko, p.lbo, p.sbo);
+                const uint64_t b0 = make_desc_mn(sa + 2 * A_PL + ko, p.lbo, p.sbo);
+                const uint64_t b1 = make_desc_mn(sa + 2 * A_PL + B_PL + ko, p.lbo, p.sbo);
+                umma_bf16(tmem_base, a0, b0, idesc, (it | kk) != 0);
+                umma_bf16(tmem_base + NCOLS, a0, b1, idesc, (it | kk) != 0);
+                umma_bf16(tmem_base + NCOLS, a1, b0, idesc, 1);
+            }
+            umma_commit(&empty[s]);
+        }
+        umma_commit(tmem_full);
+    } else if (warp >= 2) {
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3, row = q * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int m = m0 + row;
+        float* __restrict__ out = p.dw + (size_t)wg_split * p.split_stride + (size_t)wg_j * p.s_j;
+        const size_t ma = (size_t)(m % p.msplit) * p.s_m + (size_t)(m / p.msplit) * p.s_mh;
+        const bool vec = (p.s_n == 1) && ((p.Nw & 3) == 0) &&
+                         (((ma + (size_t)wg_j * p.s_j + (size_t)wg_split * p.split_stride) & 3) == 0);
+        for (int c32 = 0; c32 < NCOLS; c32 += 32) {
+            float v[32];
+            tmem_ld_add(taddr + c32, NCOLS, v);
+            if (m >= p.Mw) continue;
+            const int nn = n0 + c32;
+            if (n_iters == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            if (vec && nn + 32 <= p.Nw) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(&out[ma + nn + i]) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (nn + i < p.Nw) out[ma + (size_t)(nn + i) * p.s_n] = v[i];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<2 * NCOLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -435,15 +572,16 @@ extern "C" {
 
 int dv3_tc_k_block(void) { return tc_bk(); }
 
-// 1 if the tensor-core ConvBlock path supports this block shape (else the caller uses the exact-fp32 kernels)
+// 1 if the tensor-core ConvBlock path supports this block shape (else the caller uses the exact-fp32 kernels).
+// (Only the legacy K-major weight gradient dv3_tc_wgrad needs T % 8 == 0; the default dv3_tc_wgrad_mn does not.)
 int dv3_tc_supported(int B, int C, int T, int k) {
-    return (C % 128 == 0) && (T % 8 == 0) && k >= 1 && k <= MAX_TAPS_TC && B >= 1 && B <= 65535;
+    return (C % 128 == 0) && T >= 1 && k >= 1 && k <= MAX_TAPS_TC && B >= 1 && B <= 65535;
 }
 // plain convs: any channel counts (planes are padded to a multiple of 8 channels), T % 8 == 0; k-tap convs need
 // Cout % 128 == 0 so a weight box never straddles two taps
 int dv3_tc_conv_supported(int B, int Cin, int Cout, int T, int k) {
-    return (T % 8 == 0) && k >= 1 && k <= MAX_TAPS_TC && B >= 1 && B <= 65535 && (k == 1 || Cout % 128 == 0) &&
-           Cin >= 8 && Cout >= 1;
+    return T >= 1 && k >= 1 && k <= MAX_TAPS_TC && B >= 1 && B <= 65535 && (k == 1 || Cout % 128 == 0) && Cin >= 8 &&
+           Cout >= 1;
 }
 
 // Gated forward.  xd: [npl][B][T][C] bf16 planes of the (dropped-out) input; w: [npl][k][2C][C] bf16 planes of the
@@ -485,7 +623,7 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
                 int causal, int transpose_taps, const float* bias, int relu, float p_drop,
                 const unsigned long long* seed_ptr, unsigned salt, int addmode, const float* e1, const float* e2,
                 float alpha, void* stream) {
-    DV3_REQUIRE(T % 8 == 0 && k >= 1 && k <= MAX_TAPS_TC && (k == 1 || Nc % 128 == 0) && B <= 65535,
+    DV3_REQUIRE(k >= 1 && k <= MAX_TAPS_TC && (k == 1 || Nc % 128 == 0) && B <= 65535,
                 "tc_conv: unsupported shape B=%d Kc=%d Nc=%d T=%d k=%d", B, Kc, Nc, T, k);
     DV3_REQUIRE(npl == 2, "tc_conv: npl must be 2");
     const int bk = tc_bk();
@@ -563,6 +701,46 @@ int dv3_tc_wgrad(const void* dy, const void* xs, float* dw_partials, long long s
     dim3 grid(1, m_tiles, p.nsplit * k);
     if (bk == 64) return launch_tc<TC_WGRAD, 1, 64, 2>(maps, p, grid, st, "tc_wgrad");
     return launch_tc<TC_WGRAD, 1, 32, 2>(maps, p, grid, st, "tc_wgrad");
+}
+
+// Weight gradient from (B,T,C) planes (no shifted copies).  dy: [2][B][T][pad8(Mw)], xd: [2][B][T][pad8(Nw)].
+int dv3_tc_wgrad_mn(const void* dy, const void* xd, float* dw_partials, long long split_stride, int B, int Mw,
+                    int Nw, int T, int k, int dilation, int causal, int msplit, long long s_m, long long s_mh,
+                    long long s_n, long long s_j, void* stream) {
+    DV3_REQUIRE(k >= 1 && k <= MAX_TAPS_TC && B <= 65535, "tc_wgrad_mn: unsupported shape k=%d", k);
+    const int Mp = (Mw + 7) / 8 * 8, Np = (Nw + 7) / 8 * 8;
+    TcMaps maps;
+    for (int pl = 0; pl < 2; ++pl) {
+        if (encode_tmap_bf16_3d(&maps.a[pl], plane(dy, pl, (long long)B * T * Mp), Mw, T, B, (uint64_t)Mp * 2,
+                                (uint64_t)T * Mp * 2, 64, 32)) return 1;
+        if (encode_tmap_bf16_3d(&maps.b[pl], plane(xd, pl, (long long)B * T * Np), Nw, T, B, (uint64_t)Np * 2,
+                                (uint64_t)T * Np * 2, 64, 32)) return 1;
+    }
+    TcMnParams p = {};
+    p.T = T; p.B = B; p.Mw = Mw; p.Nw = Nw; p.k = k; p.kb_n = (T + 31) / 32;
+    fill_taps_tc(p.tap_off, k, dilation, causal, false);
+    p.nsplit = dv3_tc_wgrad_nsplit(B, Mw, Nw, T, k);
+    p.batches_per_split = (B + p.nsplit - 1) / p.nsplit;
+    p.dw = dw_partials; p.split_stride = split_stride;
+    p.msplit = msplit; p.s_m = s_m; p.s_mh = s_mh; p.s_n = s_n; p.s_j = s_j;
+    // 64-channel chunks are 4 KB apart (one TMA box each), 8-row groups 1 KB apart inside a box
+    const char* sw = getenv("DV3_TC_MN_SWAP");
+    p.lbo = 4096; p.sbo = 1024;
+    if (sw && atoi(sw) == 1) { p.lbo = 1024; p.sbo = 4096; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m_tiles = (Mw + 127) / 128;
+    if (Nw > 128) {
+        constexpr int SMEM = 4 * 2 * (2 * 4096 + 4 * 4096) + 1024 + 512;
+        static bool configured = false;
+        if (!configured) { cudaFuncSetAttribute(tc_wgrad_mn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
+        tc_wgrad_mn_kernel<2><<<dim3((Nw + 255) / 256, m_tiles, p.nsplit * k), TC_THREADS, SMEM, st>>>(maps, p);
+    } else {
+        constexpr int SMEM = 6 * 2 * (2 * 4096 + 2 * 4096) + 1024 + 512;
+        static bool configured = false;
+        if (!configured) { cudaFuncSetAttribute(tc_wgrad_mn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
+        tc_wgrad_mn_kernel<1><<<dim3(1, m_tiles, p.nsplit * k), TC_THREADS, SMEM, st>>>(maps, p);
+    }
+    return check_launch("tc_wgrad_mn");
 }
 
 }  // extern "C"

@@ -88,9 +88,11 @@ __global__ void gate_bwd_split_kernel(const float* __restrict__ dy, const float*
             const float g = dy[in] * gs, av = a[in], sv = s[in];
             da = g * sv;
             db = g * ((mode == 0) ? av : (av - x[in])) * sv * (1.f - sv);
-            const size_t oa = ((size_t)b * 2 * C + c) * T + t;
-            split_store<2>(da, bct, oa, plane);
-            split_store<2>(db, bct, oa + (size_t)C * T, plane);
+            if (bct) {
+                const size_t oa = ((size_t)b * 2 * C + c) * T + t;
+                split_store<2>(da, bct, oa, plane);
+                split_store<2>(db, bct, oa + (size_t)C * T, plane);
+            }
         }
         ta[threadIdx.y + 8 * i][threadIdx.x] = da;
         tb[threadIdx.y + 8 * i][threadIdx.x] = db;

@@ -185,6 +185,10 @@ class _ConvBlockFn(torch.autograd.Function):
         return dx, dv, dg, dbias, dspk, None, None, None, None, None, None, None
 
 
+# Weight gradients straight from the (B,T,C) planes (MN-major UMMA operands): no time-shifted (k,B,C,T) copies.
+wgrad_mn = os.environ.get("DV3_TC_WGRAD_MN", "1") == "1"
+
+
 def _fwd_planes():
     """bf16 planes per operand (hi, lo).  A 3-plane / 6-product variant was measured to be LESS accurate: the tensor
     core's truncating accumulation (one event per MMA) dominates the operand-split error (see csrc/tc_gemm.cu)."""
@@ -214,9 +218,11 @@ class _ConvBlockTCFn(torch.autograd.Function):
                  _stream())
         p, seed_ptr, salt = _drop_args(p_drop, training, dev)
         x_btc = torch.empty(npl, B, T, C, device=dev, dtype=bf)
-        x_bct = torch.empty(2, k, B, C, T, device=dev, dtype=bf) if need_bwd else None   # k shifted copies
+        x_bct = torch.empty(2, k, B, C, T, device=dev, dtype=bf) if (need_bwd and not wgrad_mn) else None
         lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, C, T, k, dilation, int(causal), p,
                  seed_ptr, salt, _stream())
+        if need_bwd and wgrad_mn:
+            x_bct = x_btc                 # the weight gradient reads the forward's own planes
         y = torch.empty_like(x)
         a = torch.empty_like(x) if need_bwd else None
         s = torch.empty_like(x) if need_bwd else None
@@ -236,7 +242,7 @@ class _ConvBlockTCFn(torch.autograd.Function):
         B, C, T = x.shape
         bf = torch.bfloat16
         d_btc = torch.empty(2, B, T, 2 * C, device=dev, dtype=bf)
-        d_bct = torch.empty(2, B, 2 * C, T, device=dev, dtype=bf)
+        d_bct = None if wgrad_mn else torch.empty(2, B, 2 * C, T, device=dev, dtype=bf)
         dbias = torch.zeros(2 * C, device=dev)
         lib.call("dv3_tc_gate_bwd_split", _p(dy), _p(a), _p(s), _p(x), _p(d_btc), _p(d_bct), _p(dbias), B, C, T,
                  mode, int(residual), _stream())
@@ -255,12 +261,19 @@ class _ConvBlockTCFn(torch.autograd.Function):
             numel = v.numel()
             partials = torch.empty(nsplit, numel, device=dev)
             # partials [split][j][2C][C]: contiguous float4 stores from the GEMM epilogue
-            lib.call("dv3_tc_wgrad", _p(d_bct), _p(x_bct), _p(partials), numel, B, 2 * C, C, T, k, 2 * C, C, 0, 1,
-                     2 * C * C, _stream())
+            if wgrad_mn:
+                lib.call("dv3_tc_wgrad_mn", _p(d_btc), _p(x_bct), _p(partials), numel, B, 2 * C, C, T, k, dilation,
+                         int(causal), 2 * C, C, 0, 1, 2 * C * C, _stream())
+            else:
+                lib.call("dv3_tc_wgrad", _p(d_bct), _p(x_bct), _p(partials), numel, B, 2 * C, C, T, k, 2 * C, C, 0,
+                         1, 2 * C * C, _stream())
             dv, dg = _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k)
         dspk = None
         if has_spk and ctx.needs_input_grad[4]:
-            dspk = d_bct[0, :, :C, :].float() + d_bct[1, :, :C, :].float()
+            if d_bct is not None:
+                dspk = d_bct[0, :, :C, :].float() + d_bct[1, :, :C, :].float()
+            else:                       # d_a = hi + lo of the (B,T,2C) planes, back to the (B,C,T) layout
+                dspk = transpose12((d_btc[0, :, :, :C].float() + d_btc[1, :, :, :C].float()).contiguous())
         return dx, dv, dg, dbias, dspk, None, None, None, None, None, None, None
 
 
@@ -284,9 +297,11 @@ class _Conv1dTCFn(torch.autograd.Function):
                  _stream())
         x_btc = torch.empty(npl, B, T, Cinp, device=dev, dtype=bf)
         need_w = need_bwd and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
-        x_bct = torch.empty(2, k, B, Cin, T, device=dev, dtype=bf) if need_w else None
+        x_bct = torch.empty(2, k, B, Cin, T, device=dev, dtype=bf) if (need_w and not wgrad_mn) else None
         lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, Cin, T, k, dilation, int(causal), 0.0,
                  None, 0, _stream())
+        if need_w and wgrad_mn:
+            x_bct = x_btc
         y = torch.empty(B, Cout, T, device=dev)
         lib.call("dv3_tc_conv", _p(x_btc), _p(wfwd), npl, _p(y), B, Cin, Cout, T, k, dilation, int(causal), 0,
                  _p(bias), int(relu), 0.0, None, 0, 0, None, None, 0.0, _stream())
@@ -304,8 +319,8 @@ class _Conv1dTCFn(torch.autograd.Function):
         Coutp = _pad8(Cout)
         need_x = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        g_btc = torch.empty(2, B, T, Coutp, device=dev, dtype=bf) if need_x else None
-        g_bct = torch.empty(2, B, Cout, T, device=dev, dtype=bf) if need_w else None
+        g_btc = torch.empty(2, B, T, Coutp, device=dev, dtype=bf) if (need_x or (need_w and wgrad_mn)) else None
+        g_bct = torch.empty(2, B, Cout, T, device=dev, dtype=bf) if (need_w and not wgrad_mn) else None
         dbias = torch.zeros(Cout, device=dev)
         lib.call("dv3_tc_grad_split", _p(dy), _p(y), _p(g_btc), _p(g_bct), _p(dbias), B, Cout, T, int(relu), _stream())
         dx = None
@@ -318,8 +333,12 @@ class _Conv1dTCFn(torch.autograd.Function):
             nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, Cout, Cin, T, k)
             numel = v.numel()
             partials = torch.empty(nsplit, numel, device=dev)
-            lib.call("dv3_tc_wgrad", _p(g_bct), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, Cout, Cin, 0, 1,
-                     Cout * Cin, _stream())
+            if wgrad_mn:
+                lib.call("dv3_tc_wgrad_mn", _p(g_btc), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, dilation,
+                         int(causal), Cout, Cin, 0, 1, Cout * Cin, _stream())
+            else:
+                lib.call("dv3_tc_wgrad", _p(g_bct), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, Cout, Cin, 0,
+                         1, Cout * Cin, _stream())
             dv, dg = _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k)
         return dx, dv, dg, dbias, None, None, None, None
 
@@ -342,8 +361,10 @@ class _ConvT2TCFn(torch.autograd.Function):
         lib.call("dv3_tc_weightnorm_convt_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), npl, _p(wbwd), Cin, Cout,
                  _stream())
         x_btc = torch.empty(npl, B, T, Cinp, device=dev, dtype=bf)
-        x_bct = torch.empty(2, 1, B, Cin, T, device=dev, dtype=bf)
+        x_bct = None if wgrad_mn else torch.empty(2, 1, B, Cin, T, device=dev, dtype=bf)
         lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, Cin, T, 1, 1, 0, 0.0, None, 0, _stream())
+        if wgrad_mn:
+            x_bct = x_btc
         bias2 = bias.repeat(2)
         yp = torch.empty(B, 2 * Cout, T, device=dev)
         lib.call("dv3_tc_conv", _p(x_btc), _p(wfwd), npl, _p(yp), B, Cin, 2 * Cout, T, 1, 1, 0, 0, _p(bias2), 0, 0.0,
@@ -364,7 +385,7 @@ class _ConvT2TCFn(torch.autograd.Function):
         dyp = torch.empty(B, 2 * Cout, T, device=dev)
         lib.call("dv3_interleave2", _p(dy), _p(dyp), B, Cout, T, 1, _stream())
         g_btc = torch.empty(2, B, T, K2p, device=dev, dtype=bf)
-        g_bct = torch.empty(2, B, 2 * Cout, T, device=dev, dtype=bf)
+        g_bct = None if wgrad_mn else torch.empty(2, B, 2 * Cout, T, device=dev, dtype=bf)
         db2 = torch.zeros(2 * Cout, device=dev)
         lib.call("dv3_tc_grad_split", _p(dyp), None, _p(g_btc), _p(g_bct), _p(db2), B, 2 * Cout, T, 0, _stream())
         dbias = db2[:Cout] + db2[Cout:]
@@ -380,8 +401,12 @@ class _ConvT2TCFn(torch.autograd.Function):
             numel = v.numel()
             partials = torch.empty(nsplit, numel, device=dev)
             # element (m=(j,co), ci) -> v layout (ci, co, j): ci*2*Cout + co*2 + j
-            lib.call("dv3_tc_wgrad", _p(g_bct), _p(x_bct), _p(partials), numel, B, M, Cin, T, 1, Cout, 2, 1, 2 * Cout,
-                     0, _stream())
+            if wgrad_mn:
+                lib.call("dv3_tc_wgrad_mn", _p(g_btc), _p(x_bct), _p(partials), numel, B, M, Cin, T, 1, 1, 0, Cout, 2, 1,
+                         2 * Cout, 0, _stream())
+            else:
+                lib.call("dv3_tc_wgrad", _p(g_bct), _p(x_bct), _p(partials), numel, B, M, Cin, T, 1, Cout, 2, 1,
+                         2 * Cout, 0, _stream())
             dv, dg = _wn_bwd(partials, nsplit, v, g, inv)
         return dx, dv, dg, dbias
 
@@ -392,7 +417,7 @@ def _use_tc_conv(x, Cin, Cout, k):
     if conv_math not in ("tc", "bf16x3") or not x.is_cuda:
         return False
     B, _, T = x.shape
-    if not lib.raw("dv3_tc_conv_supported")(B, Cin, Cout, T, int(k)):
+    if not lib.raw("dv3_tc_conv_supported")(B, Cin, Cout, T, int(k)) or not (wgrad_mn or T % 8 == 0):
         return False
     if k > 1 and Cin % 128 != 0:          # the data gradient swaps the roles of Cin / Cout
         return False
@@ -400,7 +425,8 @@ def _use_tc_conv(x, Cin, Cout, k):
 
 
 def tc_supported(B, C, T, k):
-    return bool(lib.raw("dv3_tc_supported")(B, C, T, k))
+    ok = bool(lib.raw("dv3_tc_supported")(B, C, T, k))
+    return ok and (wgrad_mn or T % 8 == 0)      # only the legacy K-major weight gradient needs T % 8 == 0
 
 
 def convblock(x, v, g, bias, spk=None, k=3, dilation=1, causal=False, mode=MODE_GLU, residual=True,

@@ -147,8 +147,8 @@ int dv3_stft_mel(const float* wav, const int* lengths, const float* mel_basis, c
  * p1*p1 + p0*p2 + p2*p0 ("x6", fp32-equivalent).  Plane buffers are bf16 device memory laid out [npl][...]; channel
  * pitches are padded to a multiple of 8.  Callers use the exact-fp32 entry points for unsupported shapes. */
 int dv3_tc_k_block(void);                                   /* K-block width in use: 32 (default) or 64 (DV3_TC_BK=64) */
-int dv3_tc_supported(int B, int C, int T, int k);           /* gated block: C % 128 == 0, T % 8 == 0, k <= 8 */
-int dv3_tc_conv_supported(int B, int Cin, int Cout, int T, int k);   /* plain conv: T % 8 == 0, (k == 1 or Cout % 128 == 0) */
+int dv3_tc_supported(int B, int C, int T, int k);           /* gated block: C % 128 == 0, k <= 8 */
+int dv3_tc_conv_supported(int B, int Cin, int Cout, int T, int k);   /* plain conv: k == 1 or Cout % 128 == 0 */
 /* x (B,C,T) fp32 -> conv-input dropout -> btc: [npl][B][T][Cp] planes (forward operand, Cp = pad8(C)) and
  * bct: [2][k][B][C][T] planes = k time-shifted zero-padded copies (weight-gradient operand; NULL to skip). */
 int dv3_tc_split_input(const float* x, void* btc, int npl, void* bct, int B, int C, int T, int k, int dilation,
@@ -179,6 +179,11 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
 /* weight gradient: dy: [2][B][Mw][T], xs: [2][k][B][Nw][T]; partial element (m,n,j) at
  * (m%msplit)*s_m + (m/msplit)*s_mh + n*s_n + j*s_j; writes dv3_tc_wgrad_nsplit(...) partials. */
 int dv3_tc_wgrad_nsplit(int B, int Mw, int Nw, int T, int k);
+/* same weight gradient computed from the (B,T,C) planes of the forward / data-gradient GEMMs (MN-major UMMA
+ * operands, tap shift = TMA row coordinate): dy: [2][B][T][pad8(Mw)], xd: [2][B][T][pad8(Nw)]; no shifted copies. */
+int dv3_tc_wgrad_mn(const void* dy, const void* xd, float* dw_partials, long long split_stride, int B, int Mw,
+                    int Nw, int T, int k, int dilation, int causal, int msplit, long long s_m, long long s_mh,
+                    long long s_n, long long s_j, void* stream);
 int dv3_tc_wgrad(const void* dy, const void* xs, float* dw_partials, long long split_stride, int B, int Mw, int Nw,
                  int T, int k, int msplit, long long s_m, long long s_mh, long long s_n, long long s_j, void* stream);
 

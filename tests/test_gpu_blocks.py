@@ -136,6 +136,8 @@ def test_plain_conv_canonical_vs_oracle(Cin, Cout, T, kind, math, monkeypatch):
 
 # ---- BASELINE.json canonical shapes against the CPU oracle ---------------------------------------
 @pytest.mark.parametrize("B,C,T,k,d,causal,residual,mode", [
+    (3, 128, 37, 3, 9, True, True, "glu"),           # ragged: T odd, single partial tile, halo > T/2
+    (2, 256, 131, 5, 3, False, True, "hw"),          # k=5, T = 128 + 3
     (16, 256, 200, 3, 27, True, False, "glu"),
     (16, 512, 128, 3, 9, False, True, "glu"),
     (4, 256, 800, 3, 3, False, True, "glu"),
