@@ -107,10 +107,9 @@ def _wn_conv_fwd(v, g):
     return w_f, w_b, inv
 
 
-def _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=0):
+def _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=0, out=None):
     """tap_major_k = 0: partials in v's layout; = k (> 0): partials as [j][R][X] (tensor-core weight gradient)."""
-    dv = torch.empty_like(v)
-    dg = torch.empty_like(g)
+    dv, dg = out if out is not None else (torch.empty_like(v), torch.empty_like(g))
     R = v.shape[0]
     if tap_major_k:
         X = v.numel() // R // tap_major_k
@@ -189,6 +188,41 @@ class _ConvBlockFn(torch.autograd.Function):
 wgrad_mn = os.environ.get("DV3_TC_WGRAD_MN", "1") == "1"
 
 
+# The weight-gradient GEMM (+ the weight-norm backward that consumes it) and the data-gradient GEMM of a block are
+# independent: run the former on a side stream so the two overlap -- most layers launch only 32-128 CTAs on 148 SMs.
+# Fork/join with stream waits, which a CUDA-graph capture records as graph edges.
+overlap_wgrad = os.environ.get("DV3_OVERLAP_WGRAD", "1") == "1"
+_side_streams = {}
+
+
+class _SideStream:
+    """with _SideStream(dev): ...   work inside is ordered after everything already on the current stream; the
+    current stream waits for it at join()."""
+
+    def __init__(self, dev):
+        self.enabled = overlap_wgrad
+        if self.enabled:
+            if dev not in _side_streams:
+                _side_streams[dev] = torch.cuda.Stream(device=dev)
+            self.side = _side_streams[dev]
+            self.main = torch.cuda.current_stream(dev)
+            self.ctx = torch.cuda.stream(self.side)
+
+    def __enter__(self):
+        if self.enabled:
+            self.side.wait_stream(self.main)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.enabled:
+            self.ctx.__exit__(*a)
+
+    def join(self):
+        if self.enabled:
+            self.main.wait_stream(self.side)
+
+
 def _fwd_planes():
     """bf16 planes per operand (hi, lo).  A 3-plane / 6-product variant was measured to be LESS accurate: the tensor
     core's truncating accumulation (one event per MMA) dominates the operand-split error (see csrc/tc_gemm.cu)."""
@@ -246,6 +280,24 @@ class _ConvBlockTCFn(torch.autograd.Function):
         dbias = torch.zeros(2 * C, device=dev)
         lib.call("dv3_tc_gate_bwd_split", _p(dy), _p(a), _p(s), _p(x), _p(d_btc), _p(d_bct), _p(dbias), B, C, T,
                  mode, int(residual), _stream())
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dv = dg = partials = None
+        if need_w:                                   # allocate on the main stream, compute on the side stream
+            nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, 2 * C, C, T, k)
+            numel = v.numel()
+            partials = torch.empty(nsplit, numel, device=dev)
+            dv, dg = torch.empty_like(v), torch.empty_like(g)
+        side = _SideStream(dev)
+        if need_w:
+            with side:
+                # partials [split][j][2C][C]: contiguous float4 stores from the GEMM epilogue
+                if wgrad_mn:
+                    lib.call("dv3_tc_wgrad_mn", _p(d_btc), _p(x_bct), _p(partials), numel, B, 2 * C, C, T, k, dilation,
+                             int(causal), 2 * C, C, 0, 1, 2 * C * C, _stream())
+                else:
+                    lib.call("dv3_tc_wgrad", _p(d_bct), _p(x_bct), _p(partials), numel, B, 2 * C, C, T, k, 2 * C, C, 0,
+                             1, 2 * C * C, _stream())
+                _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k, out=(dv, dg))
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
@@ -255,19 +307,8 @@ class _ConvBlockTCFn(torch.autograd.Function):
                 addmode, e1, e2, alpha = 2, dy, s, 0.0
             lib.call("dv3_tc_conv", _p(d_btc), _p(wbwd), 2, _p(dx), B, 2 * C, C, T, k, dilation, int(causal), 1,
                      None, 0, p, seed_ptr, salt, addmode, _p(e1), _p(e2), alpha, _stream())
-        dv = dg = None
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, 2 * C, C, T, k)
-            numel = v.numel()
-            partials = torch.empty(nsplit, numel, device=dev)
-            # partials [split][j][2C][C]: contiguous float4 stores from the GEMM epilogue
-            if wgrad_mn:
-                lib.call("dv3_tc_wgrad_mn", _p(d_btc), _p(x_bct), _p(partials), numel, B, 2 * C, C, T, k, dilation,
-                         int(causal), 2 * C, C, 0, 1, 2 * C * C, _stream())
-            else:
-                lib.call("dv3_tc_wgrad", _p(d_bct), _p(x_bct), _p(partials), numel, B, 2 * C, C, T, k, 2 * C, C, 0,
-                         1, 2 * C * C, _stream())
-            dv, dg = _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k)
+        if need_w:
+            side.join()
         dspk = None
         if has_spk and ctx.needs_input_grad[4]:
             if d_bct is not None:
@@ -323,23 +364,28 @@ class _Conv1dTCFn(torch.autograd.Function):
         g_bct = torch.empty(2, B, Cout, T, device=dev, dtype=bf) if (need_w and not wgrad_mn) else None
         dbias = torch.zeros(Cout, device=dev)
         lib.call("dv3_tc_grad_split", _p(dy), _p(y), _p(g_btc), _p(g_bct), _p(dbias), B, Cout, T, int(relu), _stream())
+        dv = dg = None
+        side = _SideStream(dev)
+        if need_w:
+            nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, Cout, Cin, T, k)
+            numel = v.numel()
+            partials = torch.empty(nsplit, numel, device=dev)
+            dv, dg = torch.empty_like(v), torch.empty_like(g)
+            with side:
+                if wgrad_mn:
+                    lib.call("dv3_tc_wgrad_mn", _p(g_btc), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, dilation,
+                             int(causal), Cout, Cin, 0, 1, Cout * Cin, _stream())
+                else:
+                    lib.call("dv3_tc_wgrad", _p(g_bct), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, Cout, Cin,
+                             0, 1, Cout * Cin, _stream())
+                _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k, out=(dv, dg))
         dx = None
         if need_x:
             dx = torch.empty(B, Cin, T, device=dev)
             lib.call("dv3_tc_conv", _p(g_btc), _p(wbwd), 2, _p(dx), B, Cout, Cin, T, k, dilation, int(causal), 1, None,
                      0, 0.0, None, 0, 0, None, None, 0.0, _stream())
-        dv = dg = None
         if need_w:
-            nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, Cout, Cin, T, k)
-            numel = v.numel()
-            partials = torch.empty(nsplit, numel, device=dev)
-            if wgrad_mn:
-                lib.call("dv3_tc_wgrad_mn", _p(g_btc), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, dilation,
-                         int(causal), Cout, Cin, 0, 1, Cout * Cin, _stream())
-            else:
-                lib.call("dv3_tc_wgrad", _p(g_bct), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, Cout, Cin, 0,
-                         1, Cout * Cin, _stream())
-            dv, dg = _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k)
+            side.join()
         return dx, dv, dg, dbias, None, None, None, None
 
 
