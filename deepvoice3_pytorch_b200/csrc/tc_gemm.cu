@@ -67,14 +67,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 
-template <int NBOX, int BK, int NPL>
+// BR = rows of one B-operand box (128, or 64 for problems too small to fill the machine with 128-wide tiles)
+template <int NBOX, int BK, int NPL, int BR = 128>
 struct TcCfg {
-    static constexpr int TILE = 128 * BK * 2;
-    static constexpr int STAGE = NPL * (1 + NBOX) * TILE;
+    static constexpr int TILE = 128 * BK * 2;            // A tile (128 rows)
+    static constexpr int TILE_B = BR * BK * 2;           // one B box
+    static constexpr int STAGE = NPL * (TILE + NBOX * TILE_B);
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
     static constexpr int SMEM = STAGES * STAGE + 1024 + 512;
-    static constexpr int NCOLS = 128 * NBOX;         // columns per accumulator; two accumulators (main, cross)
+    static constexpr int NCOLS = BR * NBOX;          // columns per accumulator; two accumulators (main, cross)
     static constexpr int TMEM_COLS = 2 * NCOLS;
 };
 
@@ -90,11 +92,12 @@ __device__ __forceinline__ void tmem_ld_add(uint32_t taddr, int cross_off, float
 // CL > 1: thread-block cluster of CL CTAs along the batch axis.  They need the same weight tiles, so CTA r fetches
 // rows [r*128/CL, (r+1)*128/CL) of every weight box and TMA-multicasts them into all CL shared memories: weight
 // bytes read from L2 per CTA drop by CL (the kernels are L2->SMEM bandwidth bound, ~3.8 TB/s measured).
-template <int MODE, int NBOX, int BK, int NPL, int CL>
+template <int MODE, int NBOX, int BK, int NPL, int CL, int BR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
-    using Cfg = TcCfg<NBOX, BK, NPL>;
-    constexpr int TILE = Cfg::TILE, STAGE = Cfg::STAGE, STAGES = Cfg::STAGES, NCOLS = Cfg::NCOLS;
+    using Cfg = TcCfg<NBOX, BK, NPL, BR>;
+    constexpr int TILE = Cfg::TILE, TILE_B = Cfg::TILE_B, STAGE = Cfg::STAGE, STAGES = Cfg::STAGES, NCOLS = Cfg::NCOLS;
+    constexpr int B_OFF = NPL * TILE;                    // B planes start after the A planes
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
@@ -108,16 +111,16 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     int a_row0, a_z = 0, b_row0, b_row1, n_iters, wg_j = 0, wg_split = 0, b_beg = 0;
     if (MODE == TC_GATED) {
         a_row0 = blockIdx.x * 128; a_z = blockIdx.z;                 // t0, batch
-        b_row0 = blockIdx.y * 128; b_row1 = p.Nc + blockIdx.y * 128; // a half, b half
+        b_row0 = blockIdx.y * BR; b_row1 = p.Nc + blockIdx.y * BR;   // a half, b half
         n_iters = p.k * p.kb_n;
     } else if (MODE == TC_CONV) {
         a_row0 = blockIdx.x * 128; a_z = blockIdx.z;
-        b_row0 = blockIdx.y * 128 * NBOX; b_row1 = b_row0 + 128;     // n0
+        b_row0 = blockIdx.y * BR * NBOX; b_row1 = b_row0 + BR;       // n0
         n_iters = p.k * p.kb_n;
     } else {
         wg_j = blockIdx.z % p.k; wg_split = blockIdx.z / p.k;
         a_row0 = blockIdx.y * 128;                                   // m0
-        b_row0 = blockIdx.x * 128 * NBOX; b_row1 = b_row0 + 128;     // n0
+        b_row0 = blockIdx.x * BR * NBOX; b_row1 = b_row0 + BR;       // n0
         b_beg = wg_split * p.batches_per_split;
         int b_end = b_beg + p.batches_per_split; if (b_end > p.B) b_end = p.B;
         n_iters = (b_end > b_beg ? b_end - b_beg : 0) * p.kb_n;
@@ -125,7 +128,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
     static_assert(CL == 1 || MODE != TC_WGRAD, "weight-gradient tiles share no operand across the batch");
     constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1);
-    constexpr int SLICE_ROWS = 128 / CL, SLICE_BYTES = SLICE_ROWS * BK * 2;
+    constexpr int SLICE_ROWS = BR / CL, SLICE_BYTES = SLICE_ROWS * BK * 2;
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
 
     if (threadIdx.x == 0) {
@@ -166,16 +169,15 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
             for (int pl = 0; pl < NPL; ++pl) {
                 tma_load_3d(st + pl * TILE, &maps.a[pl], &full[s], ax, ay, az);
+                uint8_t* bdst = st + B_OFF + pl * NBOX * TILE_B;
                 if (CL == 1) {
-                    tma_load_3d(st + (NPL + pl * NBOX) * TILE, &maps.b[pl], &full[s], bx, by0, bz);
-                    if (NBOX == 2) tma_load_3d(st + (NPL + pl * NBOX + 1) * TILE, &maps.b[pl], &full[s], bx, by1, bz);
+                    tma_load_3d(bdst, &maps.b[pl], &full[s], bx, by0, bz);
+                    if (NBOX == 2) tma_load_3d(bdst + TILE_B, &maps.b[pl], &full[s], bx, by1, bz);
                 } else {
                     const int ro = crank * SLICE_ROWS, so = crank * SLICE_BYTES;
-                    tma_load_3d_multicast(st + (NPL + pl * NBOX) * TILE + so, &maps.bs[pl], &full[s], bx, by0 + ro, bz,
-                                          CL_MASK);
+                    tma_load_3d_multicast(bdst + so, &maps.bs[pl], &full[s], bx, by0 + ro, bz, CL_MASK);
                     if (NBOX == 2)
-                        tma_load_3d_multicast(st + (NPL + pl * NBOX + 1) * TILE + so, &maps.bs[pl], &full[s], bx,
-                                              by1 + ro, bz, CL_MASK);
+                        tma_load_3d_multicast(bdst + TILE_B + so, &maps.bs[pl], &full[s], bx, by1 + ro, bz, CL_MASK);
                 }
             }
         }
@@ -191,7 +193,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
             for (int pl = 0; pl < NPL; ++pl) {
                 da[pl] = make_desc<BK>(sa + pl * TILE);
-                db[pl] = make_desc<BK>(sa + (NPL + pl * NBOX) * TILE);
+                db[pl] = make_desc<BK>(sa + B_OFF + pl * NBOX * TILE_B);
             }
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
@@ -227,10 +229,10 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             float* __restrict__ so = p.save_s;
             const bool need_res = (p.gate_mode != 0) || p.residual;
             const size_t base = ((size_t)b * C + b_row0) * p.T + (tv ? t : 0);
-            for (int c32 = 0; c32 < 128; c32 += 32) {
+            for (int c32 = 0; c32 < BR; c32 += 32) {
                 float va[32], vb[32], rr[32];
                 tmem_ld_add(taddr + c32, NCOLS, va);
-                tmem_ld_add(taddr + 128 + c32, NCOLS, vb);
+                tmem_ld_add(taddr + BR + c32, NCOLS, vb);
                 if (!tv) continue;
                 const size_t cb = base + (size_t)c32 * p.T;
 #pragma unroll
@@ -500,12 +502,12 @@ int encode_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_
     return 0;
 }
 
-template <int MODE, int NBOX, int BK, int NPL, int CL = 1>
+template <int MODE, int NBOX, int BK, int NPL, int CL = 1, int BR = 128>
 static int launch_tc(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStream_t st, const char* what) {
-    using Cfg = TcCfg<NBOX, BK, NPL>;
+    using Cfg = TcCfg<NBOX, BK, NPL, BR>;
     static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
     static bool configured = false;
-    auto kern = tc_conv_kernel<MODE, NBOX, BK, NPL, CL>;
+    auto kern = tc_conv_kernel<MODE, NBOX, BK, NPL, CL, BR>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) {
@@ -594,11 +596,15 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
     const int bk = tc_bk();
     TcMaps maps;
     const int cl = pick_cluster(B);
+    const int t_tiles = (T + 127) / 128;
+    // 64-channel tiles (64 a | 64 b columns) when 128-channel tiles would leave most of the 148 SMs idle
+    const bool half = bk == 32 && cl == 1 && (long long)t_tiles * (C / 128) * B < 100;
+    const int br = half ? 64 : 128;
     for (int pl = 0; pl < npl; ++pl) {
         if (encode_tmap_bf16_3d(&maps.a[pl], plane(xd, pl, (long long)B * T * C), C, T, B, (uint64_t)C * 2,
                                 (uint64_t)T * C * 2, bk, 128)) return 1;
         if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
-                                (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 128)) return 1;
+                                (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, br)) return 1;
         if (cl > 1 && encode_tmap_bf16_3d(&maps.bs[pl], plane(w, pl, (long long)k * 2 * C * C), C,
                                           (uint64_t)k * 2 * C, 1, (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk,
                                           128 / cl)) return 1;
@@ -608,8 +614,9 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
     fill_taps_tc(p.tap_off, k, dilation, causal, false);
     p.bias = bias; p.spk = spk; p.res = res; p.y = y; p.save_a = save_a; p.save_s = save_s;
     p.gate_mode = mode; p.residual = residual;
-    dim3 grid((T + 127) / 128, C / 128, B);
+    dim3 grid(t_tiles, C / br, B);
     cudaStream_t st = (cudaStream_t)stream;
+    if (half) return launch_tc<TC_GATED, 2, 32, 2, 1, 64>(maps, p, grid, st, "tc_convblock_fwd(64)");
     if (bk == 64) return launch_tc<TC_GATED, 2, 64, 2>(maps, p, grid, st, "tc_convblock_fwd");
     if (cl == 4) return launch_tc<TC_GATED, 2, 32, 2, 4>(maps, p, grid, st, "tc_convblock_fwd(cluster4)");
     if (cl == 2) return launch_tc<TC_GATED, 2, 32, 2, 2>(maps, p, grid, st, "tc_convblock_fwd(cluster2)");
@@ -630,11 +637,17 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
     const int Kp = (Kc + 7) / 8 * 8;
     TcMaps maps;
     const int cl = pick_cluster(B);
+    const int t_tiles = (T + 127) / 128;
+    // tile width: two 128-column boxes only when that still fills the machine; 64 columns for small problems
+    const bool wide = Nc > 128 && (long long)t_tiles * ((Nc + 255) / 256) * B >= 120;
+    const bool narrow = !wide && bk == 32 && cl == 1 && Nc > 64 && (k == 1 || Nc % 64 == 0) &&
+                        (long long)t_tiles * ((Nc + 127) / 128) * B < 100;
+    const int br = narrow ? 64 : 128;
     for (int pl = 0; pl < npl; ++pl) {
         if (encode_tmap_bf16_3d(&maps.a[pl], plane(a, pl, (long long)B * T * Kp), Kc, T, B, (uint64_t)Kp * 2,
                                 (uint64_t)T * Kp * 2, bk, 128)) return 1;
         if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
-                                (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, 128)) return 1;
+                                (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, br)) return 1;
         if (cl > 1 && encode_tmap_bf16_3d(&maps.bs[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
                                           (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, 128 / cl)) return 1;
     }
@@ -644,9 +657,10 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
     p.out = out; p.bias = bias; p.relu = relu; p.e1 = e1; p.e2 = e2; p.alpha = alpha; p.addmode = addmode;
     p.p_drop = p_drop; p.seed_ptr = seed_ptr; p.salt = salt;
     cudaStream_t st = (cudaStream_t)stream;
-    const int t_tiles = (T + 127) / 128;
-    // two 128-column boxes per CTA only when that still fills the machine
-    const bool wide = Nc > 128 && (long long)t_tiles * ((Nc + 255) / 256) * B >= 120;
+    if (narrow) {
+        dim3 grid(t_tiles, (Nc + 63) / 64, B);
+        return launch_tc<TC_CONV, 1, 32, 2, 1, 64>(maps, p, grid, st, "tc_conv(64)");
+    }
     if (wide) {
         dim3 grid(t_tiles, (Nc + 255) / 256, B);
         if (bk == 64) return launch_tc<TC_CONV, 2, 64, 2>(maps, p, grid, st, "tc_conv");
