@@ -230,7 +230,11 @@ def convblock_roofline(dev, pk, pk_kind):
     flops = 2.0 * Bc * T * 2 * C * C * k
     r = {
         "bound": "hbm", "kernel": "%s (B=16,C=512,T=800,k=3)" % name, "achieved": alg_bytes / t / 1e9,
-        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / t / 1e9 / pk["hbm_gbs"], "traffic": None,
+        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / t / 1e9 / pk["hbm_gbs"],
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed
+        # `ncu --set full` capture (profiles/r01_ncu_full_tc_convblock_v2.csv): 59.9 MB + 32.0 MB per launch
+        # (it also reads the bf16 hi/lo planes of the input: 2 x 13.1 MB, and writes y + the two saved gate tensors)
+        "traffic": 91.95e6 if math != "fp32" else None,
         "peak_source": pk_kind, "launch_us": t * 1e6, "alg_bytes": alg_bytes, "math": math,
         # the block is a dense contraction (686 FLOP/B): the binding roof is arithmetic, reported beside the HBM one
         "fp32_equiv_tflops": flops / t / 1e12,
