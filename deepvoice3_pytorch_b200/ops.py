@@ -248,18 +248,21 @@ class _ConvBlockTCFn(torch.autograd.Function):
         scale = torch.empty_like(inv)
         wfwd = torch.empty(npl, k, 2 * C, C, device=dev, dtype=bf)
         wbwd = torch.empty(2, k, C, 2 * C, device=dev, dtype=bf)
-        lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), npl, _p(wbwd), 2 * C, C, k,
-                 _stream())
         p, seed_ptr, salt = _drop_args(p_drop, training, dev)
         x_btc = torch.empty(npl, B, T, C, device=dev, dtype=bf)
         x_bct = torch.empty(2, k, B, C, T, device=dev, dtype=bf) if (need_bwd and not wgrad_mn) else None
-        lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, C, T, k, dilation, int(causal), p,
-                 seed_ptr, salt, _stream())
-        if need_bwd and wgrad_mn:
-            x_bct = x_btc                 # the weight gradient reads the forward's own planes
         y = torch.empty_like(x)
         a = torch.empty_like(x) if need_bwd else None
         s = torch.empty_like(x) if need_bwd else None
+        side = _SideStream(dev)
+        with side:                        # weight norm + split depends only on the parameters: overlap it with
+            lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), npl, _p(wbwd), 2 * C, C, k,
+                     _stream())           # the activation split below
+        lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, C, T, k, dilation, int(causal), p,
+                 seed_ptr, salt, _stream())
+        side.join()
+        if need_bwd and wgrad_mn:
+            x_bct = x_btc                 # the weight gradient reads the forward's own planes
         lib.call("dv3_tc_convblock_fwd", _p(x_btc), _p(wfwd), npl, _p(bias), _p(spk), _p(x), _p(y), _p(a), _p(s),
                  B, C, T, k, dilation, int(causal), mode, int(residual), _stream())
         if need_bwd:
@@ -334,16 +337,19 @@ class _Conv1dTCFn(torch.autograd.Function):
         scale = torch.empty_like(inv)
         wfwd = torch.empty(npl, k, Cout, Cinp, device=dev, dtype=bf)
         wbwd = torch.empty(2, k, Cin, Coutp, device=dev, dtype=bf)
-        lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), npl, _p(wbwd), Cout, Cin, k,
-                 _stream())
         x_btc = torch.empty(npl, B, T, Cinp, device=dev, dtype=bf)
         need_w = need_bwd and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         x_bct = torch.empty(2, k, B, Cin, T, device=dev, dtype=bf) if (need_w and not wgrad_mn) else None
+        y = torch.empty(B, Cout, T, device=dev)
+        side = _SideStream(dev)
+        with side:
+            lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), npl, _p(wbwd), Cout, Cin, k,
+                     _stream())
         lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, Cin, T, k, dilation, int(causal), 0.0,
                  None, 0, _stream())
+        side.join()
         if need_w and wgrad_mn:
             x_bct = x_btc
-        y = torch.empty(B, Cout, T, device=dev)
         lib.call("dv3_tc_conv", _p(x_btc), _p(wfwd), npl, _p(y), B, Cin, Cout, T, k, dilation, int(causal), 0,
                  _p(bias), int(relu), 0.0, None, 0, 0, None, None, 0.0, _stream())
         if need_bwd:
