@@ -74,6 +74,8 @@ struct TcCfg {
     static constexpr int TILE_B = BR * BK * 2;           // one B box
     static constexpr int STAGE = NPL * (TILE + NBOX * TILE_B);
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048) / STAGE;
+    // (measured: 3 stages + 2 CTAs/SM for the 64-row variants -- epilogue of one CTA overlapping the K loop of the
+    // other -- is 8-13 % faster on the big shapes but 7-9 % slower on the small ones they exist for; not kept)
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
     static constexpr int SMEM = STAGES * STAGE + 1024 + 512;
     static constexpr int NCOLS = BR * NBOX;          // columns per accumulator; two accumulators (main, cross)
@@ -598,7 +600,9 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
     const int cl = pick_cluster(B);
     const int t_tiles = (T + 127) / 128;
     // 64-channel tiles (64 a | 64 b columns) when 128-channel tiles would leave most of the 148 SMs idle
-    const bool half = bk == 32 && cl == 1 && (long long)t_tiles * (C / 128) * B < 100;
+    static int force_half = -1;
+    if (force_half < 0) { const char* e = getenv("DV3_TC_FORCE_HALF"); force_half = (e && atoi(e) == 1) ? 1 : 0; }
+    const bool half = bk == 32 && cl == 1 && (force_half || (long long)t_tiles * (C / 128) * B < 100);
     const int br = half ? 64 : 128;
     for (int pl = 0; pl < npl; ++pl) {
         if (encode_tmap_bf16_3d(&maps.a[pl], plane(xd, pl, (long long)B * T * C), C, T, B, (uint64_t)C * 2,
