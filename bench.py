@@ -227,25 +227,30 @@ def convblock_roofline(dev, pk, pk_kind):
         ts.append(s.elapsed_time(e) * 1e-3)
     t = float(np.mean(ts))
     alg_bytes = 4.0 * (2 * Bc * C * T + 2 * C * C * k + 4 * C)
-    flops = 2.0 * Bc * T * 2 * C * C * k
-    r = {
-        "bound": "hbm", "kernel": "%s (B=16,C=512,T=800,k=3)" % name, "achieved": alg_bytes / t / 1e9,
-        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / t / 1e9 / pk["hbm_gbs"],
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed
-        # `ncu --set full` capture (profiles/r01_ncu_full_tc_convblock_v2.csv): 59.9 MB + 32.0 MB per launch
-        # (it also reads the bf16 hi/lo planes of the input: 2 x 13.1 MB, and writes y + the two saved gate tensors)
-        "traffic": 91.95e6 if math != "fp32" else None,
-        "peak_source": pk_kind, "launch_us": t * 1e6, "alg_bytes": alg_bytes, "math": math,
-        # the block is a dense contraction (686 FLOP/B): the binding roof is arithmetic, reported beside the HBM one
-        "fp32_equiv_tflops": flops / t / 1e12,
-    }
+    flops = 2.0 * Bc * T * 2 * C * C * k                     # algorithmic (fp32) flops of the block forward
+    hbm = {"bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+           "frac": alg_bytes / t / 1e9 / pk["hbm_gbs"], "alg_bytes": alg_bytes,
+           "note": "BASELINE.json's 'ConvBlock HBM GB/s': algorithmic bytes / launch time; the block is a dense "
+                   "contraction (686 FLOP/B here), so this roof does not bind"}
     if mma_passes:
-        r["tensor"] = {"bound": "tensor", "achieved": mma_passes * flops / t / 1e12, "peak": pk["bf16_tflops"],
-                       "unit": "TFLOP/s", "frac": mma_passes * flops / t / 1e12 / pk["bf16_tflops"],
-                       "note": "bf16 MMA work actually issued = 3 passes (hi*hi, hi*lo, lo*hi) of the fp32-equivalent flops"}
+        # the binding roof: tensor cores.  `achieved` counts the ALGORITHMIC flops (one fp32 multiply-add per term);
+        # the kernel issues 3 bf16 MMA passes per term (hi*hi, hi*lo, lo*hi) to be fp32-accurate, reported beside it.
+        r = {"bound": "tensor", "kernel": "%s (B=16,C=512,T=800,k=3)" % name, "achieved": flops / t / 1e12,
+             "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": flops / t / 1e12 / pk["bf16_tflops"],
+             "issued_bf16_tflops": mma_passes * flops / t / 1e12,
+             "issued_frac": mma_passes * flops / t / 1e12 / pk["bf16_tflops"],
+             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed
+             # `ncu --set full` capture (profiles/r01_ncu_full_tc_convblock_v2.csv): 59.9 MB + 32.0 MB per launch
+             # (it reads the bf16 hi/lo planes of the input and writes y + the two saved gate tensors)
+             "traffic": 91.95e6, "peak_source": pk_kind, "launch_us": t * 1e6, "alg_flops": flops, "math": math,
+             "hbm": hbm}
     else:
-        r["fp32_fma"] = {"achieved": flops / t / 1e12, "peak": 74.5, "unit": "TFLOP/s", "frac": flops / t / 1e12 / 74.5,
-                         "note": "nominal fp32 FMA peak 148 SM x 128 lanes x 2 x 1.965 GHz"}
+        r = dict(hbm, kernel="%s (B=16,C=512,T=800,k=3)" % name, traffic=None, peak_source=pk_kind,
+                 launch_us=t * 1e6, math=math,
+                 fp32_fma={"achieved": flops / t / 1e12, "peak": 74.5, "unit": "TFLOP/s",
+                           "frac": flops / t / 1e12 / 74.5,
+                           "note": "nominal fp32 FMA peak 148 SM x 128 lanes x 2 x 1.965 GHz (the binding roof of "
+                                   "the exact-fp32 mode)"})
     return r
 
 
