@@ -60,45 +60,43 @@ __global__ void wn_pack_kernel(const float* __restrict__ v, const float* __restr
 // (one warp per row left the big layers -- 1024 rows x 1536 x up to 16 partials -- at 0.4 TB/s.)
 // Partials are either in v's own layout (jmajor_X == 0: element e of row r at r*L + e) or tap-major
 // (jmajor_X = X > 0: element (r, x, j) at (j*R + r)*X + x -- what the tensor-core weight-gradient kernel writes with
-// contiguous float4 stores).
-__global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ dw_partials, long long split_stride,
+// contiguous float4 stores).  The reduced dW is parked in partial slot 0 between the two passes, so dv / dg can be
+// ACCUMULATED into (accumulate = 1: the flat gradient arena of the training step, no autograd add kernel afterwards).
+__global__ void __launch_bounds__(256) wn_bwd_kernel(float* __restrict__ dw_partials, long long split_stride,
                                                      int nsplit, int jmajor_X, const float* __restrict__ v,
                                                      const float* __restrict__ g,
                                                      const float* __restrict__ inv_norm, float* __restrict__ dv,
-                                                     float* __restrict__ dg, int R, int L) {
+                                                     float* __restrict__ dg, int R, int L, int accumulate) {
     __shared__ float red[8];
     __shared__ float s_dot;
     const int r = blockIdx.x, tid = threadIdx.x;
     const size_t base = (size_t)r * L;
+    const int X = jmajor_X > 0 ? jmajor_X : L, k = L / X;
     float dot = 0.f;
-    const bool vec = ((L & 3) == 0) && ((split_stride & 3) == 0) && jmajor_X == 0;
-    if (jmajor_X > 0) {
-        const int X = jmajor_X, k = L / X;
-        for (int q = tid; q < L; q += 256) {             // q = j*X + x: coalesced over the partials
-            const int j = q / X, x = q - j * X, e = x * k + j;
+    const bool vec4 = jmajor_X > 0 && (X & 3) == 0 && (split_stride & 3) == 0;
+    if (vec4) {                                          // tap-major partials: float4 along x, v gathered at stride k
+        const int X4 = X >> 2;
+        for (int q = tid; q < k * X4; q += 256) {
+            const int j = q / X4, x = (q - j * X4) << 2;
             const size_t po = ((size_t)j * R + r) * X + x;
-            float d = 0.f;
-            for (int s = 0; s < nsplit; ++s) d += dw_partials[(size_t)s * split_stride + po];
-            dv[base + e] = d;
-            dot = fmaf(d, v[base + e], dot);
-        }
-    } else if (vec) {
-        const int L4 = L >> 2;
-        for (int e = tid; e < L4; e += 256) {
             float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int s = 0; s < nsplit; ++s) {
-                const float4 q = *reinterpret_cast<const float4*>(&dw_partials[(size_t)s * split_stride + base + 4 * e]);
-                d.x += q.x; d.y += q.y; d.z += q.z; d.w += q.w;
+                const float4 t = *reinterpret_cast<const float4*>(&dw_partials[(size_t)s * split_stride + po]);
+                d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
             }
-            const float4 vv = *reinterpret_cast<const float4*>(&v[base + 4 * e]);
-            *reinterpret_cast<float4*>(&dv[base + 4 * e]) = d;
-            dot = fmaf(d.x, vv.x, dot); dot = fmaf(d.y, vv.y, dot); dot = fmaf(d.z, vv.z, dot); dot = fmaf(d.w, vv.w, dot);
+            *reinterpret_cast<float4*>(&dw_partials[po]) = d;
+            const float* vv = v + base + (size_t)x * k + j;
+            dot = fmaf(d.x, vv[0], dot); dot = fmaf(d.y, vv[k], dot);
+            dot = fmaf(d.z, vv[2 * k], dot); dot = fmaf(d.w, vv[3 * k], dot);
         }
     } else {
-        for (int e = tid; e < L; e += 256) {
+        for (int q = tid; q < L; q += 256) {             // q runs over the partial's own (coalesced) order
+            size_t po; int e;
+            if (jmajor_X > 0) { const int j = q / X, x = q - j * X; e = x * k + j; po = ((size_t)j * R + r) * X + x; }
+            else { e = q; po = base + q; }
             float d = 0.f;
-            for (int s = 0; s < nsplit; ++s) d += dw_partials[(size_t)s * split_stride + base + e];
-            dv[base + e] = d;
+            for (int s = 0; s < nsplit; ++s) d += dw_partials[(size_t)s * split_stride + po];
+            dw_partials[po] = d;
             dot = fmaf(d, v[base + e], dot);
         }
     }
@@ -113,25 +111,14 @@ __global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ d
     __syncthreads();
     dot = s_dot;
     const float inv = inv_norm[r], sc = g[r] * inv, c2 = sc * dot * inv * inv;
-    // each thread rewrites exactly the elements it stored above
-    if (jmajor_X > 0) {
-        const int X = jmajor_X, k = L / X;
-        for (int q = tid; q < L; q += 256) {             // same thread -> same elements as in the first pass
-            const int j = q / X, x = q - j * X, e = x * k + j;
-            dv[base + e] = sc * dv[base + e] - c2 * v[base + e];
-        }
-    } else if (vec) {
-        const int L4 = L >> 2;
-        for (int e = tid; e < L4; e += 256) {
-            float4 d = *reinterpret_cast<float4*>(&dv[base + 4 * e]);
-            const float4 vv = *reinterpret_cast<const float4*>(&v[base + 4 * e]);
-            d.x = sc * d.x - c2 * vv.x; d.y = sc * d.y - c2 * vv.y; d.z = sc * d.z - c2 * vv.z; d.w = sc * d.w - c2 * vv.w;
-            *reinterpret_cast<float4*>(&dv[base + 4 * e]) = d;
-        }
-    } else {
-        for (int e = tid; e < L; e += 256) dv[base + e] = sc * dv[base + e] - c2 * v[base + e];
+    for (int q = tid; q < L; q += 256) {                 // same thread -> same elements as in the first pass
+        size_t po; int e;
+        if (jmajor_X > 0) { const int j = q / X, x = q - j * X; e = x * k + j; po = ((size_t)j * R + r) * X + x; }
+        else { e = q; po = base + q; }
+        const float val = sc * dw_partials[po] - c2 * v[base + e];
+        dv[base + e] = accumulate ? dv[base + e] + val : val;
     }
-    if (tid == 0) dg[r] = dot * inv;
+    if (tid == 0) dg[r] = accumulate ? dg[r] + dot * inv : dot * inv;
 }
 
 }  // namespace dv3
@@ -154,12 +141,13 @@ int dv3_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* s
     return check_launch("weightnorm_fwd(pack)");
 }
 
-// dw_partials: [nsplit][R*X*k]; tap_major = 0: v's own layout (r, x, j); 1: [j][r][x].
-int dv3_weightnorm_bwd(const float* dw_partials, long long split_stride, int nsplit, int tap_major,
-                       const float* v, const float* g, const float* inv_norm, float* dv, float* dg, int R, int X,
-                       int k, void* stream) {
+// dw_partials: [nsplit][R*X*k] (slot 0 is overwritten with the reduced dW); tap_major = 0: v's own layout
+// (r, x, j); 1: [j][r][x].  accumulate = 1 adds into dv / dg instead of overwriting them.
+int dv3_weightnorm_bwd(float* dw_partials, long long split_stride, int nsplit, int tap_major, const float* v,
+                       const float* g, const float* inv_norm, float* dv, float* dg, int R, int X, int k,
+                       int accumulate, void* stream) {
     wn_bwd_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(
-        dw_partials, split_stride, nsplit, tap_major ? X : 0, v, g, inv_norm, dv, dg, R, X * k);
+        dw_partials, split_stride, nsplit, tap_major ? X : 0, v, g, inv_norm, dv, dg, R, X * k, accumulate);
     return check_launch("weightnorm_bwd");
 }
 

@@ -107,18 +107,32 @@ def _wn_conv_fwd(v, g):
     return w_f, w_b, inv
 
 
-def _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=0, out=None):
+# Gradient sink (set by train_step.TrainStep): parameter gradients are accumulated by the kernels straight into the
+# pre-allocated ``.grad`` views of the flat gradient arena and the autograd Functions return None for them, which
+# removes one ``grad += new`` elementwise kernel per parameter per step (~130 launches).  Off by default: plain
+# autograd semantics (Functions return dv, dg, dbias).
+grad_sink = False
+
+
+def _sink(*params):
+    """The .grad buffers to accumulate into, or None when the sink is off / not every buffer exists."""
+    if not grad_sink or any(p.grad is None or not p.grad.is_contiguous() for p in params):
+        return None
+    return [p.grad for p in params]
+
+
+def _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=0, out=None, accumulate=False):
     """tap_major_k = 0: partials in v's layout; = k (> 0): partials as [j][R][X] (tensor-core weight gradient)."""
     dv, dg = out if out is not None else (torch.empty_like(v), torch.empty_like(g))
     R = v.shape[0]
     if tap_major_k:
         X = v.numel() // R // tap_major_k
         lib.call("dv3_weightnorm_bwd", _p(partials), v.numel(), nsplit, 1, _p(v), _p(g), _p(inv), _p(dv), _p(dg), R, X,
-                 tap_major_k, _stream())
+                 tap_major_k, int(accumulate), _stream())
     else:
         X = v.numel() // R
         lib.call("dv3_weightnorm_bwd", _p(partials), v.numel(), nsplit, 0, _p(v), _p(g), _p(inv), _p(dv), _p(dg), R, X,
-                 1, _stream())
+                 1, int(accumulate), _stream())
     return dv, dg
 
 
@@ -268,6 +282,7 @@ class _ConvBlockTCFn(torch.autograd.Function):
         if need_bwd:
             ctx.save_for_backward(x, v, g, a, s, x_bct, wbwd, inv)
             ctx.cfg = (k, dilation, causal, mode, residual, p, salt, spk is not None, dev)
+            ctx.bias_param = bias if bias.is_leaf else None
         return y
 
     @staticmethod
@@ -280,7 +295,8 @@ class _ConvBlockTCFn(torch.autograd.Function):
         bf = torch.bfloat16
         d_btc = torch.empty(2, B, T, 2 * C, device=dev, dtype=bf)
         d_bct = None if wgrad_mn else torch.empty(2, B, 2 * C, T, device=dev, dtype=bf)
-        dbias = torch.zeros(2 * C, device=dev)
+        sink = _sink(v, g, ctx.bias_param) if ctx.bias_param is not None else None
+        dbias = sink[2] if sink else torch.zeros(2 * C, device=dev)
         lib.call("dv3_tc_gate_bwd_split", _p(dy), _p(a), _p(s), _p(x), _p(d_btc), _p(d_bct), _p(dbias), B, C, T,
                  mode, int(residual), _stream())
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
@@ -289,7 +305,7 @@ class _ConvBlockTCFn(torch.autograd.Function):
             nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, 2 * C, C, T, k)
             numel = v.numel()
             partials = torch.empty(nsplit, numel, device=dev)
-            dv, dg = torch.empty_like(v), torch.empty_like(g)
+            dv, dg = (sink[0], sink[1]) if sink else (torch.empty_like(v), torch.empty_like(g))
         side = _SideStream(dev)
         if need_w:
             with side:
@@ -300,7 +316,7 @@ class _ConvBlockTCFn(torch.autograd.Function):
                 else:
                     lib.call("dv3_tc_wgrad", _p(d_bct), _p(x_bct), _p(partials), numel, B, 2 * C, C, T, k, 2 * C, C, 0,
                              1, 2 * C * C, _stream())
-                _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k, out=(dv, dg))
+                _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k, out=(dv, dg), accumulate=bool(sink))
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
@@ -312,6 +328,8 @@ class _ConvBlockTCFn(torch.autograd.Function):
                      None, 0, p, seed_ptr, salt, addmode, _p(e1), _p(e2), alpha, _stream())
         if need_w:
             side.join()
+        if sink:                                     # already accumulated into the .grad arena views
+            dv = dg = dbias = None
         dspk = None
         if has_spk and ctx.needs_input_grad[4]:
             if d_bct is not None:
@@ -355,6 +373,7 @@ class _Conv1dTCFn(torch.autograd.Function):
         if need_bwd:
             ctx.save_for_backward(v, g, x_bct, wbwd, inv, y if relu else None)
             ctx.cfg = (B, Cin, Cout, T, k, dilation, causal, relu)
+            ctx.bias_param = bias if bias.is_leaf else None
         return y
 
     @staticmethod
@@ -368,7 +387,8 @@ class _Conv1dTCFn(torch.autograd.Function):
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         g_btc = torch.empty(2, B, T, Coutp, device=dev, dtype=bf) if (need_x or (need_w and wgrad_mn)) else None
         g_bct = torch.empty(2, B, Cout, T, device=dev, dtype=bf) if (need_w and not wgrad_mn) else None
-        dbias = torch.zeros(Cout, device=dev)
+        sink = _sink(v, g, ctx.bias_param) if (ctx.bias_param is not None and v.is_leaf and g.is_leaf) else None
+        dbias = sink[2] if sink else torch.zeros(Cout, device=dev)
         lib.call("dv3_tc_grad_split", _p(dy), _p(y), _p(g_btc), _p(g_bct), _p(dbias), B, Cout, T, int(relu), _stream())
         dv = dg = None
         side = _SideStream(dev)
@@ -376,7 +396,7 @@ class _Conv1dTCFn(torch.autograd.Function):
             nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, Cout, Cin, T, k)
             numel = v.numel()
             partials = torch.empty(nsplit, numel, device=dev)
-            dv, dg = torch.empty_like(v), torch.empty_like(g)
+            dv, dg = (sink[0], sink[1]) if sink else (torch.empty_like(v), torch.empty_like(g))
             with side:
                 if wgrad_mn:
                     lib.call("dv3_tc_wgrad_mn", _p(g_btc), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, dilation,
@@ -384,7 +404,7 @@ class _Conv1dTCFn(torch.autograd.Function):
                 else:
                     lib.call("dv3_tc_wgrad", _p(g_bct), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, Cout, Cin,
                              0, 1, Cout * Cin, _stream())
-                _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k, out=(dv, dg))
+                _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k, out=(dv, dg), accumulate=bool(sink))
         dx = None
         if need_x:
             dx = torch.empty(B, Cin, T, device=dev)
@@ -392,6 +412,8 @@ class _Conv1dTCFn(torch.autograd.Function):
                      0, 0.0, None, 0, 0, None, None, 0.0, _stream())
         if need_w:
             side.join()
+        if sink:
+            dv = dg = dbias = None
         return dx, dv, dg, dbias, None, None, None, None
 
 

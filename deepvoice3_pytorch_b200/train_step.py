@@ -244,6 +244,13 @@ class TrainStep:
     # -- pieces -------------------------------------------------------------------------------
     def _forward_backward(self, batch):
         self.arena.zero_grad()
+        ops.grad_sink = True          # kernels accumulate parameter gradients straight into the arena
+        try:
+            return self._forward_backward_inner(batch)
+        finally:
+            ops.grad_sink = False
+
+    def _forward_backward_inner(self, batch):
         outs = self.model(batch["x"], batch["mel"], speaker_ids=batch.get("speaker_ids"),
                           text_positions=batch["text_positions"], frame_positions=batch["frame_positions"],
                           input_lengths=batch["input_lengths_dev"])

@@ -36,11 +36,12 @@ long long dv3_launch_count(void);
 int dv3_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* scale, float* out1,
                        float* out2, int R, int X, int k, long long s1r, long long s1x, long long s1j,
                        long long s2r, long long s2x, long long s2j, void* stream);
-/* dw_partials: [nsplit][R*X*k] partial gradients w.r.t. w (summed here), in v's own layout (r,x,j) when
- * tap_major = 0 or as [j][r][x] when tap_major = 1; outputs dv [R][X][k], dg [R]. */
-int dv3_weightnorm_bwd(const float* dw_partials, long long split_stride, int nsplit, int tap_major,
-                       const float* v, const float* g, const float* inv_norm, float* dv, float* dg, int R, int X,
-                       int k, void* stream);
+/* dw_partials: [nsplit][R*X*k] partial gradients w.r.t. w (summed here; slot 0 is overwritten with the sum), in
+ * v's own layout (r,x,j) when tap_major = 0 or as [j][r][x] when tap_major = 1; outputs dv [R][X][k], dg [R],
+ * overwritten (accumulate = 0) or added to (accumulate = 1, e.g. straight into a flat gradient arena). */
+int dv3_weightnorm_bwd(float* dw_partials, long long split_stride, int nsplit, int tap_major, const float* v,
+                       const float* g, const float* inv_norm, float* dv, float* dg, int R, int X, int k,
+                       int accumulate, void* stream);
 
 /* ---- fused ConvBlock forward: reference modules.py:145-164 (Conv1dGLU._forward, mode 0) and
  * modules.py:200-226 (HighwayConv1d._forward, mode 1).
