@@ -92,3 +92,40 @@ def test_training_loss_matches_oracle_and_step_runs():
         assert float((step.arena.flat - before).abs().max()) > 0
         assert float(step.opt.grad_norm().item()) > 0
         ops.check_index_errors()
+
+
+@pytest.mark.gpu
+def test_gradient_sink_equals_autograd():
+    """TrainStep lets the kernels accumulate parameter gradients straight into the flat arena (ops.grad_sink) instead
+    of returning them to autograd: both routes must give the same gradients (tensor-core and exact-fp32 modes)."""
+    from deepvoice3_pytorch_b200 import builder, ops
+    from deepvoice3_pytorch_b200.train_step import ParameterArena, make_synthetic_batch, to_device, fused_training_loss
+    kw = dict(n_vocab=149, embed_dim=64, mel_dim=80, linear_dim=129, r=1, downsample_step=4, kernel_size=3,
+              encoder_channels=128, decoder_channels=128, converter_channels=128, use_memory_mask=True,
+              key_projection=True, value_projection=True, dropout=0.0, max_positions=256)
+    dev = to_device(make_synthetic_batch(B=2, T_text=24, T_mel=64, linear_dim=129, seed=9), "cuda")
+    old_math = ops.conv_math
+    try:
+        for math in ("tc", "fp32"):
+            ops.conv_math = math
+            torch.manual_seed(0)
+            model = builder.deepvoice3(**kw).cuda().train()
+            arena = ParameterArena(model)
+
+            def run(sink):
+                arena.zero_grad()
+                ops.grad_sink = sink
+                try:
+                    outs = model(dev["x"], dev["mel"], text_positions=dev["text_positions"],
+                                 frame_positions=dev["frame_positions"], input_lengths=dev["input_lengths_dev"])
+                    fused_training_loss(outs, dev).backward()
+                finally:
+                    ops.grad_sink = False
+                torch.cuda.synchronize()
+                return arena.grad.clone()
+
+            g_autograd, g_sink = run(False), run(True)
+            assert float(g_autograd.abs().max()) > 0
+            torch.testing.assert_close(g_sink, g_autograd, rtol=1e-5, atol=1e-7)
+    finally:
+        ops.conv_math = old_math
