@@ -485,6 +485,10 @@ class _ConvT2TCFn(torch.autograd.Function):
         return dx, dv, dg, dbias
 
 
+# 16 keeps the 16-wide speaker projections of the multi-speaker model on tensor cores (measured: vctk step 11.8 -> 10.6 ms)
+TC_MIN_CHANNELS = int(os.environ.get("DV3_TC_MIN_CHANNELS", "16"))
+
+
 def _use_tc_conv(x, Cin, Cout, k):
     """Tensor cores for plain convs when the mode asks for it, the shape is supported and the GEMM is big enough to
     amortise the operand-split passes."""
@@ -495,7 +499,7 @@ def _use_tc_conv(x, Cin, Cout, k):
         return False
     if k > 1 and Cin % 128 != 0:          # the data gradient swaps the roles of Cin / Cout
         return False
-    return min(Cin, Cout) >= 32 and B * T >= 512
+    return min(Cin, Cout) >= TC_MIN_CHANNELS and B * T >= 512
 
 
 def tc_supported(B, C, T, k):
