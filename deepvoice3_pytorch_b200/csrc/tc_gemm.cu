@@ -682,11 +682,22 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
 int dv3_tc_wgrad_nsplit(int B, int Mw, int Nw, int T, int k) {
     const int nt = Nw > 128 ? (Nw + 255) / 256 : 1;
     const int tiles = ((Mw + 127) / 128) * nt * k;
-    int want = (2 * 148 + tiles - 1) / tiles;
-    if (want > B) want = B;
-    if (want < 1) want = 1;
-    const int bps = (B + want - 1) / want;
-    return (B + bps - 1) / bps;
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("DV3_TC_WGRAD_CTAS"); forced = e ? atoi(e) : 0; }
+    // split (b,t) over enough CTAs for two waves, unless that leaves each CTA fewer than ~64 K-iterations (then the
+    // per-CTA prologue/epilogue and the extra partial traffic cost more than the parallelism buys: one wave).
+    // Measured on the preset shapes (tools/tc_time.py): (512,800) prefers 296, (256,800)/(512,128)/(256,200) prefer 148.
+    const int kb_n = (T + 31) / 32;
+    int best = 1;
+    for (int target = forced > 0 ? forced : 2 * 148; target >= 148; target -= 148) {
+        int want = (target + tiles - 1) / tiles;
+        if (want > B) want = B;
+        if (want < 1) want = 1;
+        const int bps = (B + want - 1) / want;
+        best = (B + bps - 1) / bps;
+        if (forced > 0 || bps * kb_n >= 64) break;
+    }
+    return best;
 }
 
 // Weight gradient.  dy: [2][B][Mw][T] bf16 planes; xs: [2][k][B][Nw][T] bf16 planes (k time-shifted copies of the

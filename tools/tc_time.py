@@ -24,7 +24,9 @@ for (B, C, T, k, d) in [(16, 512, 800, 3, 1), (16, 256, 800, 3, 3), (16, 512, 12
     rows = {}
     for e in prof.key_averages():
         if "tc_conv_kernel" in e.key:
-            rows[e.key.split("tc_conv_kernel")[1][:14]] = e.device_time_total / e.count
+            rows[e.key.split("tc_conv_kernel")[1][:18]] = e.device_time_total / e.count
+        elif "tc_wgrad_mn" in e.key or "wn_bwd" in e.key:
+            rows[e.key.split("dv3::")[-1][:18]] = e.device_time_total / e.count
     flops = 2.0 * B * T * 2 * C * C * k
     print("B=%d C=%d T=%d: " % (B, C, T) + "  ".join("%s %.1f us (%.0f TF)" % (kk, vv, flops / vv / 1e6)
                                                       for kk, vv in sorted(rows.items())), flush=True)
