@@ -91,6 +91,94 @@ __device__ __forceinline__ void tmem_ld_add(uint32_t taddr, int cross_off, float
     for (int i = 0; i < 32; ++i) v[i] += c[i];
 }
 
+// ---- epilogues (shared by the one-tile-per-CTA and the persistent kernels) ---------------------------------
+// NOTE on the epilogue loads: residual / addend / bias reads go through __ldg (ld.global.nc) and are issued as a
+// batch of 32 independent loads BEFORE the dependent math and stores of the chunk.  With plain loads the compiler
+// must order every load after the previous iteration's stores (possible aliasing), which serialised 128
+// global-memory round trips per thread and made the epilogue as long as the whole K loop (ncu: 40 % of the stall
+// samples sat on the first use of these loads).
+template <int BR, int NCOLS>
+__device__ __forceinline__ void epilogue_gated(const TcParams& p, uint32_t taddr, int a_row0, int a_z, int b_row0,
+                                               int row) {
+        const int t = a_row0 + row, b = a_z, C = p.Nc;
+        const bool tv = t < p.T;
+        const float* __restrict__ bias = p.bias;
+        const float* __restrict__ res = p.res;
+        const float* __restrict__ spk = p.spk;
+        float* __restrict__ yo = p.y;
+        float* __restrict__ ao = p.save_a;
+        float* __restrict__ so = p.save_s;
+        const bool need_res = (p.gate_mode != 0) || p.residual;
+        const size_t base = ((size_t)b * C + b_row0) * p.T + (tv ? t : 0);
+        for (int c32 = 0; c32 < BR; c32 += 32) {
+            float va[32], vb[32], rr[32];
+            tmem_ld_add(taddr + c32, NCOLS, va);
+            tmem_ld_add(taddr + BR + c32, NCOLS, vb);
+            if (!tv) continue;
+            const size_t cb = base + (size_t)c32 * p.T;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) rr[i] = need_res ? __ldg(&res[cb + (size_t)i * p.T]) : 0.f;
+            if (spk) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) va[i] += __ldg(&spk[cb + (size_t)i * p.T]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int c = b_row0 + c32 + i;
+                const size_t idx = cb + (size_t)i * p.T;
+                const float a = va[i] + __ldg(&bias[c]);
+                const float s = sigmoidf_(vb[i] + __ldg(&bias[C + c]));
+                float y;
+                if (p.gate_mode == 0) {
+                    y = a * s;
+                    if (p.residual) y = (y + rr[i]) * 0.70710678118654752f;
+                } else {
+                    y = s * a + (1.f - s) * rr[i];
+                }
+                yo[idx] = y;
+                if (ao) ao[idx] = a;
+                if (so) so[idx] = s;
+            }
+        }
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t taddr, int a_row0, int a_z, int b_row0,
+                                              int row) {
+        const int t = a_row0 + row, b = a_z;
+        const bool tv = t < p.T;
+        const DropCfg drop = make_drop(p.p_drop, p.seed_ptr, p.salt);
+        const float* __restrict__ bias = p.bias;
+        const float* __restrict__ e1 = p.e1;
+        const float* __restrict__ e2 = p.e2;
+        float* __restrict__ out = p.out;
+        for (int c32 = 0; c32 < NCOLS; c32 += 32) {
+            float v[32], x1[32], x2[32];
+            tmem_ld_add(taddr + c32, NCOLS, v);
+            if (!tv) continue;
+            const int n0 = b_row0 + c32;
+            const size_t cb = ((size_t)b * p.Nc + n0) * p.T + t;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const bool ok = n0 + i < p.Nc;
+                x1[i] = (p.addmode != 0 && ok) ? __ldg(&e1[cb + (size_t)i * p.T]) : 0.f;
+                x2[i] = (p.addmode == 2 && ok) ? __ldg(&e2[cb + (size_t)i * p.T]) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int n = n0 + i;
+                if (n >= p.Nc) continue;
+                const size_t idx = cb + (size_t)i * p.T;
+                float g = v[i] * drop_scale(drop, (uint32_t)idx);
+                if (bias) g += __ldg(&bias[n]);
+                if (p.addmode == 1) g += p.alpha * x1[i];
+                else if (p.addmode == 2) g += x1[i] * (1.f - x2[i]);
+                if (p.relu) g = fmaxf(g, 0.f);
+                out[idx] = g;
+            }
+        }
+}
+
 // CL > 1: thread-block cluster of CL CTAs along the batch axis.  They need the same weight tiles, so CTA r fetches
 // rows [r*128/CL, (r+1)*128/CL) of every weight box and TMA-multicasts them into all CL shared memories: weight
 // bytes read from L2 per CTA drop by CL (the kernels are L2->SMEM bandwidth bound, ~3.8 TB/s measured).
@@ -215,85 +303,10 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int q = warp & 3;                                      // TMEM lane quarter this warp may touch
         const int row = q * 32 + lane;                               // accumulator row (M index)
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        // NOTE on the epilogue loads: residual / addend / bias reads go through __ldg (ld.global.nc) and are issued
-        // as a batch of 32 independent loads BEFORE the dependent math and stores of the chunk.  With plain loads the
-        // compiler must order every load after the previous iteration's stores (possible aliasing), which serialised
-        // 128 global-memory round trips per thread and made the epilogue as long as the whole K loop (ncu: 40 % of
-        // the stall samples sat on the first use of these loads).
         if (MODE == TC_GATED) {
-            const int t = a_row0 + row, b = a_z, C = p.Nc;
-            const bool tv = t < p.T;
-            const float* __restrict__ bias = p.bias;
-            const float* __restrict__ res = p.res;
-            const float* __restrict__ spk = p.spk;
-            float* __restrict__ yo = p.y;
-            float* __restrict__ ao = p.save_a;
-            float* __restrict__ so = p.save_s;
-            const bool need_res = (p.gate_mode != 0) || p.residual;
-            const size_t base = ((size_t)b * C + b_row0) * p.T + (tv ? t : 0);
-            for (int c32 = 0; c32 < BR; c32 += 32) {
-                float va[32], vb[32], rr[32];
-                tmem_ld_add(taddr + c32, NCOLS, va);
-                tmem_ld_add(taddr + BR + c32, NCOLS, vb);
-                if (!tv) continue;
-                const size_t cb = base + (size_t)c32 * p.T;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) rr[i] = need_res ? __ldg(&res[cb + (size_t)i * p.T]) : 0.f;
-                if (spk) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) va[i] += __ldg(&spk[cb + (size_t)i * p.T]);
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int c = b_row0 + c32 + i;
-                    const size_t idx = cb + (size_t)i * p.T;
-                    const float a = va[i] + __ldg(&bias[c]);
-                    const float s = sigmoidf_(vb[i] + __ldg(&bias[C + c]));
-                    float y;
-                    if (p.gate_mode == 0) {
-                        y = a * s;
-                        if (p.residual) y = (y + rr[i]) * 0.70710678118654752f;
-                    } else {
-                        y = s * a + (1.f - s) * rr[i];
-                    }
-                    yo[idx] = y;
-                    if (ao) ao[idx] = a;
-                    if (so) so[idx] = s;
-                }
-            }
+            epilogue_gated<BR, NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
         } else if (MODE == TC_CONV) {
-            const int t = a_row0 + row, b = a_z;
-            const bool tv = t < p.T;
-            const DropCfg drop = make_drop(p.p_drop, p.seed_ptr, p.salt);
-            const float* __restrict__ bias = p.bias;
-            const float* __restrict__ e1 = p.e1;
-            const float* __restrict__ e2 = p.e2;
-            float* __restrict__ out = p.out;
-            for (int c32 = 0; c32 < NCOLS; c32 += 32) {
-                float v[32], x1[32], x2[32];
-                tmem_ld_add(taddr + c32, NCOLS, v);
-                if (!tv) continue;
-                const int n0 = b_row0 + c32;
-                const size_t cb = ((size_t)b * p.Nc + n0) * p.T + t;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const bool ok = n0 + i < p.Nc;
-                    x1[i] = (p.addmode != 0 && ok) ? __ldg(&e1[cb + (size_t)i * p.T]) : 0.f;
-                    x2[i] = (p.addmode == 2 && ok) ? __ldg(&e2[cb + (size_t)i * p.T]) : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int n = n0 + i;
-                    if (n >= p.Nc) continue;
-                    const size_t idx = cb + (size_t)i * p.T;
-                    float g = v[i] * drop_scale(drop, (uint32_t)idx);
-                    if (bias) g += __ldg(&bias[n]);
-                    if (p.addmode == 1) g += p.alpha * x1[i];
-                    else if (p.addmode == 2) g += x1[i] * (1.f - x2[i]);
-                    if (p.relu) g = fmaxf(g, 0.f);
-                    out[idx] = g;
-                }
-            }
+            epilogue_conv<NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
         } else {
             const int m = a_row0 + row;
             float* __restrict__ out = p.dw + (size_t)wg_split * p.split_stride + (size_t)wg_j * p.s_j;
@@ -327,6 +340,150 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     __syncthreads();
     if (CL > 1) cluster_sync_all();          // no CTA may exit while peers still multicast into / signal it
     if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent variant of the GATED / CONV kernels: one CTA per SM walks a static round-robin list of output tiles.
+// TMEM holds TWO accumulator sets (main + cross each), so the epilogue warps drain tile n (TMEM -> gate math ->
+// stores) while the MMA thread already accumulates tile n+1, and the shared-memory ring keeps streaming across tile
+// boundaries; barrier / TMEM / tensor-map set-up is paid once per SM instead of once per tile.
+// N per tile is limited to 128 columns (4 x 128 = 512 TMEM columns).
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int NBOX, int BR>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_persist_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p, int tiles_x,
+                       int tiles_y, int num_tiles) {
+    constexpr int BK = 32, NPL = 2;
+    using Cfg = TcCfg<NBOX, BK, NPL, BR>;
+    constexpr int TILE = Cfg::TILE, TILE_B = Cfg::TILE_B, STAGE = Cfg::STAGE, STAGES = Cfg::STAGES, NCOLS = Cfg::NCOLS;
+    constexpr int B_OFF = NPL * TILE;
+    static_assert(4 * NCOLS <= 512, "two accumulator sets of (main + cross) must fit in TMEM");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;          // [2] accumulator set ready for the epilogue
+    uint64_t* tempty = tfull + 2;              // [2] accumulator set drained
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_iters = p.k * p.kb_n;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.a[1]); prefetch_tmap(&maps.b[0]); prefetch_tmap(&maps.b[1]);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<4 * NCOLS>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // tile id -> (time tile, channel tile, batch); channel tiles vary fastest so that concurrently running CTAs share
+    // the activation tile in L2
+    auto decode = [&](int tile, int& a_row0, int& a_z, int& b_row0, int& b_row1) {
+        const int ty = tile % tiles_y, r = tile / tiles_y;
+        const int tx = r % tiles_x;
+        a_z = r / tiles_x;
+        a_row0 = tx * 128;
+        if (MODE == TC_GATED) { b_row0 = ty * BR; b_row1 = p.Nc + ty * BR; }
+        else { b_row0 = ty * BR * NBOX; b_row1 = b_row0 + BR; }
+    };
+
+    if (warp == 0 && lane == 0) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int a_row0, a_z, b_row0, b_row1;
+            decode(tile, a_row0, a_z, b_row0, b_row1);
+            for (int kit = 0; kit < n_iters; ++kit, ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * STAGE;
+                const int j = kit / p.kb_n, kb = kit - j * p.kb_n;
+                const int ax = kb * BK, ay = a_row0 + p.tap_off[j];
+                const int by0 = j * p.rows_per_tap + b_row0, by1 = j * p.rows_per_tap + b_row1;
+                mbar_arrive_expect_tx(&full[s], STAGE);
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) {
+                    tma_load_3d(st + pl * TILE, &maps.a[pl], &full[s], ax, ay, a_z);
+                    uint8_t* bdst = st + B_OFF + pl * NBOX * TILE_B;
+                    tma_load_3d(bdst, &maps.b[pl], &full[s], ax, by0, 0);
+                    if (NBOX == 2) tma_load_3d(bdst + TILE_B, &maps.b[pl], &full[s], ax, by1, 0);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, NCOLS);
+        int it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            const int a = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait(&tempty[a], aph ^ 1);                         // the epilogue has drained this accumulator set
+            tc_fence_after();
+            const uint32_t acc = tmem_base + a * 2 * NCOLS;
+            for (int kit = 0; kit < n_iters; ++kit, ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE);
+                const uint64_t da0 = make_desc<BK>(sa), da1 = make_desc<BK>(sa + TILE);
+                const uint64_t db0 = make_desc<BK>(sa + B_OFF), db1 = make_desc<BK>(sa + B_OFF + NBOX * TILE_B);
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; ++kk) {
+                    const uint64_t adv = (uint64_t)(kk * 2);
+                    umma_bf16(acc, da0 + adv, db0 + adv, idesc, (kit | kk) != 0);
+                    umma_bf16(acc + NCOLS, da0 + adv, db1 + adv, idesc, (kit | kk) != 0);
+                    umma_bf16(acc + NCOLS, da1 + adv, db0 + adv, idesc, 1);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(&tfull[a]);
+        }
+    } else if (warp >= 2) {
+        const int q = warp & 3, row = q * 32 + lane;
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            int a_row0, a_z, b_row0, b_row1;
+            decode(tile, a_row0, a_z, b_row0, b_row1);
+            const int a = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait(&tfull[a], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + a * 2 * NCOLS + ((uint32_t)(q * 32) << 16);
+            if (MODE == TC_GATED) epilogue_gated<BR, NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+            else epilogue_conv<NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+            tc_fence_before();
+            mbar_arrive(&tempty[a]);                                // 128 arrivals release the set to the MMA thread
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<4 * NCOLS>(tmem_base);
+}
+
+template <int MODE, int NBOX, int BR>
+static int launch_tc_persist(const TcMaps& maps, const TcParams& p, int tiles_x, int tiles_y, int batch,
+                             cudaStream_t st, const char* what) {
+    using Cfg = TcCfg<NBOX, 32, 2, BR>;
+    constexpr int SMEM = Cfg::STAGES * Cfg::STAGE + 1024 + 512;
+    static bool configured = false;
+    auto kern = tc_conv_persist_kernel<MODE, NBOX, BR>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) { set_error("%s: cannot set %d B dynamic smem: %s", what, SMEM, cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int num_tiles = tiles_x * tiles_y * batch;
+    const int grid = num_tiles < sms ? num_tiles : sms;
+    kern<<<grid, TC_THREADS, SMEM, st>>>(maps, p, tiles_x, tiles_y, num_tiles);
+    return check_launch(what);
+}
+
+static int g_persist = -1;
+static int tc_persist() {                  // DV3_TC_PERSIST=0 disables the persistent kernels
+    if (g_persist < 0) { const char* e = getenv("DV3_TC_PERSIST"); g_persist = (e && atoi(e) == 0) ? 0 : 1; }
+    return g_persist;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -620,6 +777,14 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
     p.gate_mode = mode; p.residual = residual;
     dim3 grid(t_tiles, C / br, B);
     cudaStream_t st = (cudaStream_t)stream;
+    // more tiles than SMs: the persistent kernel (64 a | 64 b columns per tile, double-buffered accumulators)
+    if (tc_persist() && bk == 32 && cl == 1 && (long long)t_tiles * (C / 64) * B > 148) {
+        if (encode_tmap_bf16_3d(&maps.b[0], plane(w, 0, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
+                                (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 64)) return 1;
+        if (encode_tmap_bf16_3d(&maps.b[1], plane(w, 1, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
+                                (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 64)) return 1;
+        return launch_tc_persist<TC_GATED, 2, 64>(maps, p, t_tiles, C / 64, B, st, "tc_convblock_fwd(persistent)");
+    }
     if (half) return launch_tc<TC_GATED, 2, 32, 2, 1, 64>(maps, p, grid, st, "tc_convblock_fwd(64)");
     if (bk == 64) return launch_tc<TC_GATED, 2, 64, 2>(maps, p, grid, st, "tc_convblock_fwd");
     if (cl == 4) return launch_tc<TC_GATED, 2, 32, 2, 4>(maps, p, grid, st, "tc_convblock_fwd(cluster4)");
@@ -661,6 +826,15 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
     p.out = out; p.bias = bias; p.relu = relu; p.e1 = e1; p.e2 = e2; p.alpha = alpha; p.addmode = addmode;
     p.p_drop = p_drop; p.seed_ptr = seed_ptr; p.salt = salt;
     cudaStream_t st = (cudaStream_t)stream;
+    if (tc_persist() && bk == 32 && cl == 1 && (long long)t_tiles * ((Nc + 127) / 128) * B > 148) {
+        // more 128-column tiles than SMs: persistent kernel with double-buffered accumulators
+        if (br != 128) {
+            for (int pl = 0; pl < 2; ++pl)
+                if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
+                                        (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, 128)) return 1;
+        }
+        return launch_tc_persist<TC_CONV, 1, 128>(maps, p, t_tiles, (Nc + 127) / 128, B, st, "tc_conv(persistent)");
+    }
     if (narrow) {
         dim3 grid(t_tiles, (Nc + 63) / 64, B);
         return launch_tc<TC_CONV, 1, 32, 2, 1, 64>(maps, p, grid, st, "tc_conv(64)");

@@ -25,6 +25,8 @@ for (B, C, T, k, d) in [(16, 512, 800, 3, 1), (16, 256, 800, 3, 3), (16, 512, 12
     for e in prof.key_averages():
         if "tc_conv_kernel" in e.key:
             rows[e.key.split("tc_conv_kernel")[1][:18]] = e.device_time_total / e.count
+        elif "tc_conv_persist" in e.key:
+            rows["persist" + e.key.split("tc_conv_persist_kernel")[1][:10]] = e.device_time_total / e.count
         elif "tc_wgrad_mn" in e.key or "wn_bwd" in e.key:
             rows[e.key.split("dv3::")[-1][:18]] = e.device_time_total / e.count
     flops = 2.0 * B * T * 2 * C * C * k
