@@ -274,6 +274,8 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     } else if (warp == 1 && lane == 0) {
         // ================= MMA issuer =================
         constexpr uint32_t idesc = make_idesc_bf16(128, NCOLS);
+        constexpr bool MERGE_HI = NPL == 2 && 2 * NCOLS <= 256;
+        constexpr uint32_t idesc2 = make_idesc_bf16(128, MERGE_HI ? 2 * NCOLS : NCOLS);
         for (int it = 0; it < n_iters; ++it) {
             const int s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(&full[s], ph);
@@ -288,8 +290,14 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
                 const uint64_t adv = (uint64_t)(kk * 2);             // 16 bf16 = 32 bytes, in 16-byte units
-                umma_bf16(tmem_base, da[0] + adv, db[0] + adv, idesc, (it | kk) != 0);          // main accumulator
-                umma_bf16(tmem_base + NCOLS, da[0] + adv, db[1] + adv, idesc, (it | kk) != 0);  // cross accumulator
+                if (MERGE_HI) {
+                    // p0 x [p0 ; p1]: the two weight planes sit back to back in the stage, so ONE N = 2*NCOLS MMA
+                    // fills the main | cross accumulators and reads the activation tile from shared memory once
+                    umma_bf16(tmem_base, da[0] + adv, db[0] + adv, idesc2, (it | kk) != 0);
+                } else {
+                    umma_bf16(tmem_base, da[0] + adv, db[0] + adv, idesc, (it | kk) != 0);          // main accumulator
+                    umma_bf16(tmem_base + NCOLS, da[0] + adv, db[1] + adv, idesc, (it | kk) != 0);  // cross accumulator
+                }
                 umma_bf16(tmem_base + NCOLS, da[1] + adv, db[0] + adv, idesc, 1);
             }
             if (CL == 1) umma_commit(&empty[s]);                     // frees the stage once these MMAs retire
@@ -414,7 +422,7 @@ tc_conv_persist_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
             }
         }
     } else if (warp == 1 && lane == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(128, NCOLS);
+        constexpr uint32_t idesc = make_idesc_bf16(128, NCOLS), idesc2 = make_idesc_bf16(128, 2 * NCOLS);
         int it = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const int a = tcount & 1, aph = (tcount >> 1) & 1;
@@ -427,12 +435,11 @@ tc_conv_persist_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + s * STAGE);
                 const uint64_t da0 = make_desc<BK>(sa), da1 = make_desc<BK>(sa + TILE);
-                const uint64_t db0 = make_desc<BK>(sa + B_OFF), db1 = make_desc<BK>(sa + B_OFF + NBOX * TILE_B);
+                const uint64_t db0 = make_desc<BK>(sa + B_OFF);         // plane 1 follows plane 0: rows [NCOLS, 2 NCOLS)
 #pragma unroll
                 for (int kk = 0; kk < BK / 16; ++kk) {
                     const uint64_t adv = (uint64_t)(kk * 2);
-                    umma_bf16(acc, da0 + adv, db0 + adv, idesc, (kit | kk) != 0);
-                    umma_bf16(acc + NCOLS, da0 + adv, db1 + adv, idesc, (kit | kk) != 0);
+                    umma_bf16(acc, da0 + adv, db0 + adv, idesc2, (kit | kk) != 0);     // p0 x [p0 ; p1] -> main | cross
                     umma_bf16(acc + NCOLS, da1 + adv, db0 + adv, idesc, 1);
                 }
                 umma_commit(&empty[s]);
@@ -484,6 +491,192 @@ static int g_persist = -1;
 static int tc_persist() {                  // DV3_TC_PERSIST=0 disables the persistent kernels
     if (g_persist < 0) { const char* e = getenv("DV3_TC_PERSIST"); g_persist = (e && atoi(e) == 0) ? 0 : 1; }
     return g_persist;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tap-reuse variant of the persistent kernel (k > 1).  ncu on the kernels above: both the gated forward and the MN
+// weight gradient move ~10 TB/s from L2 into shared memory (l1tex__m_xbar2l1tex_read_bytes / duration) -- the
+// fabric limit -- while the tensor pipe idles ~45 % of the time: the kernels are L2->SM bound, and a third to a half
+// of that traffic is the SAME activation rows fetched once per tap.  Here one pipeline stage holds, for one
+// 32-channel slice, the activation rows [t0 + off_min, t0 + off_max + 128) ONCE (a single TMA box of
+// 128 + (k-1)*dilation rows) plus the k weight boxes; tap j's MMAs read the A operand through a descriptor whose
+// start address is advanced by (off_j - off_min) rows of 64 bytes.  (SWIZZLE_64B is a function of the absolute
+// shared-memory address bits, so a row-shifted start inside a 512-byte-aligned tile addresses exactly what TMA
+// wrote.)  L2->SM bytes per output tile drop from k*(A + B) to A*(1 + span/128) + k*B.
+// The stage geometry depends on k and the dilation, so stage size / count are run-time values.
+// ------------------------------------------------------------------------------------------------
+struct TapGeom { int a_rows, a_plane, b_box, stage, stages, off_min, base_off; };
+
+template <int NBOX, int BR>
+static TapGeom tap_geom(int k, const int* tap_off) {
+    int lo = tap_off[0], hi = tap_off[0];
+    for (int j = 1; j < k; ++j) { lo = tap_off[j] < lo ? tap_off[j] : lo; hi = tap_off[j] > hi ? tap_off[j] : hi; }
+    TapGeom g;
+    g.off_min = lo;
+    g.a_rows = (128 + (hi - lo) + 7) / 8 * 8;
+    g.a_plane = (g.a_rows * 64 + 1023) / 1024 * 1024;
+    g.b_box = BR * 64;
+    g.stage = 2 * g.a_plane + 2 * k * NBOX * g.b_box;
+    g.stages = (SMEM_LIMIT - 2048) / g.stage;
+    if (g.stages > 6) g.stages = 6;
+    // debugging aid: DV3_TC_TAPS_BASEOFF=1 also writes (start >> 7) & 7 into the descriptor's base-offset field
+    static int bo = -1;
+    if (bo < 0) { const char* e = getenv("DV3_TC_TAPS_BASEOFF"); bo = (e && atoi(e) == 1) ? 1 : 0; }
+    g.base_off = bo;
+    return g;
+}
+
+template <int MODE, int NBOX, int BR>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_taps_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p,
+                    const __grid_constant__ TapGeom g, int tiles_x, int tiles_y, int num_tiles) {
+    constexpr int BK = 32, NPL = 2;
+    constexpr int NCOLS = BR * NBOX;
+    static_assert(4 * NCOLS <= 512, "two accumulator sets of (main + cross) must fit in TMEM");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int STAGES = g.stages, STAGE = g.stage;
+    const int B_OFF = NPL * g.a_plane;                 // weight boxes: [tap][plane][box]
+    const int B_PLANE = p.k * NBOX * g.b_box;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_iters = p.kb_n;                         // one stage per 32-channel slice, all taps inside
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.a[1]); prefetch_tmap(&maps.b[0]); prefetch_tmap(&maps.b[1]);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<4 * NCOLS>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto decode = [&](int tile, int& a_row0, int& a_z, int& b_row0, int& b_row1) {
+        const int ty = tile % tiles_y, r = tile / tiles_y;
+        const int tx = r % tiles_x;
+        a_z = r / tiles_x;
+        a_row0 = tx * 128;
+        if (MODE == TC_GATED) { b_row0 = ty * BR; b_row1 = p.Nc + ty * BR; }
+        else { b_row0 = ty * BR * NBOX; b_row1 = b_row0 + BR; }
+    };
+
+    if (warp == 0 && lane == 0) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int a_row0, a_z, b_row0, b_row1;
+            decode(tile, a_row0, a_z, b_row0, b_row1);
+            for (int kb = 0; kb < n_iters; ++kb, ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * STAGE;
+                const int ax = kb * BK;
+                mbar_arrive_expect_tx(&full[s], NPL * (g.a_rows * 64 + B_PLANE));
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) {
+                    tma_load_3d(st + pl * g.a_plane, &maps.a[pl], &full[s], ax, a_row0 + g.off_min, a_z);
+                    for (int j = 0; j < p.k; ++j) {
+                        uint8_t* bdst = st + B_OFF + (j * NPL + pl) * NBOX * g.b_box;
+                        tma_load_3d(bdst, &maps.b[pl], &full[s], ax, j * p.rows_per_tap + b_row0, 0);
+                        if (NBOX == 2)
+                            tma_load_3d(bdst + g.b_box, &maps.b[pl], &full[s], ax, j * p.rows_per_tap + b_row1, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, NCOLS), idesc2 = make_idesc_bf16(128, 2 * NCOLS);
+        int it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            const int a = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait(&tempty[a], aph ^ 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + a * 2 * NCOLS;
+            for (int kb = 0; kb < n_iters; ++kb, ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE);
+                for (int j = 0; j < p.k; ++j) {
+                    const uint32_t ashift = (uint32_t)(p.tap_off[j] - g.off_min) * 64u;
+                    uint64_t da0 = make_desc<BK>(sa + ashift), da1 = make_desc<BK>(sa + g.a_plane + ashift);
+                    if (g.base_off) {
+                        da0 |= (uint64_t)(((sa + ashift) >> 7) & 7) << 49;
+                        da1 |= (uint64_t)(((sa + g.a_plane + ashift) >> 7) & 7) << 49;
+                    }
+                    const uint64_t db0 = make_desc<BK>(sa + B_OFF + j * NPL * NBOX * g.b_box);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        umma_bf16(acc, da0 + adv, db0 + adv, idesc2, (kb | j | kk) != 0);   // p0 x [p0 ; p1]
+                        umma_bf16(acc + NCOLS, da1 + adv, db0 + adv, idesc, 1);
+                    }
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(&tfull[a]);
+        }
+    } else if (warp >= 2) {
+        const int q = warp & 3, row = q * 32 + lane;
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            int a_row0, a_z, b_row0, b_row1;
+            decode(tile, a_row0, a_z, b_row0, b_row1);
+            const int a = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait(&tfull[a], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + a * 2 * NCOLS + ((uint32_t)(q * 32) << 16);
+            if (MODE == TC_GATED) epilogue_gated<BR, NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+            else epilogue_conv<NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+            tc_fence_before();
+            mbar_arrive(&tempty[a]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<4 * NCOLS>(tmem_base);
+}
+
+template <int MODE, int NBOX, int BR>
+static int launch_tc_taps(const TcMaps& maps, const TcParams& p, const TapGeom& g, int tiles_x, int tiles_y, int batch,
+                          cudaStream_t st, const char* what) {
+    static bool configured = false;
+    auto kern = tc_conv_taps_kernel<MODE, NBOX, BR>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) { set_error("%s: cannot set %d B dynamic smem: %s", what, SMEM_LIMIT, cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int num_tiles = tiles_x * tiles_y * batch;
+    const int grid = num_tiles < sms ? num_tiles : sms;
+    const int smem = g.stages * g.stage + 1024 + 512;
+    kern<<<grid, TC_THREADS, smem, st>>>(maps, p, g, tiles_x, tiles_y, num_tiles);
+    return check_launch(what);
+}
+
+static int g_taps = -1;
+static int tc_taps() {                     // DV3_TC_TAPS: 0 = off, 1 = when there are more tiles than SMs, 2 = always
+    if (g_taps < 0) { const char* e = getenv("DV3_TC_TAPS"); g_taps = e ? atoi(e) : 1; }
+    return g_taps;
+}
+
+// usable when every tap fits one TMA box (<= 256 rows) and at least two stages fit in shared memory.  Measured
+// (tools/tc_time.py): 7-10 % faster than the per-tap persistent kernel on the (16,512,800) blocks, on par at
+// (16,256,800), 2-4 % slower on the <= 148-tile shapes (coarser stages, longer pipeline fill) -> default = mode 1.
+template <int NBOX, int BR>
+static bool taps_usable(int k, const int* tap_off, long long num_tiles) {
+    const int mode = tc_taps();
+    if (mode <= 0 || k < 2 || (mode == 1 && num_tiles <= 148)) return false;
+    const TapGeom g = tap_geom<NBOX, BR>(k, tap_off);
+    return g.a_rows <= 256 && g.stages >= 2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -777,6 +970,17 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
     p.gate_mode = mode; p.residual = residual;
     dim3 grid(t_tiles, C / br, B);
     cudaStream_t st = (cudaStream_t)stream;
+    // k > 1: the tap-reuse kernel (activation rows fetched once per 32-channel slice instead of once per tap)
+    if (bk == 32 && cl == 1 && taps_usable<2, 64>(k, p.tap_off, (long long)t_tiles * (C / 64) * B)) {
+        const TapGeom g = tap_geom<2, 64>(k, p.tap_off);
+        for (int pl = 0; pl < 2; ++pl) {
+            if (encode_tmap_bf16_3d(&maps.a[pl], plane(xd, pl, (long long)B * T * C), C, T, B, (uint64_t)C * 2,
+                                    (uint64_t)T * C * 2, bk, g.a_rows)) return 1;
+            if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
+                                    (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 64)) return 1;
+        }
+        return launch_tc_taps<TC_GATED, 2, 64>(maps, p, g, t_tiles, C / 64, B, st, "tc_convblock_fwd(taps)");
+    }
     // more tiles than SMs: the persistent kernel (64 a | 64 b columns per tile, double-buffered accumulators)
     if (tc_persist() && bk == 32 && cl == 1 && (long long)t_tiles * (C / 64) * B > 148) {
         if (encode_tmap_bf16_3d(&maps.b[0], plane(w, 0, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
@@ -826,6 +1030,23 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
     p.out = out; p.bias = bias; p.relu = relu; p.e1 = e1; p.e2 = e2; p.alpha = alpha; p.addmode = addmode;
     p.p_drop = p_drop; p.seed_ptr = seed_ptr; p.salt = salt;
     cudaStream_t st = (cudaStream_t)stream;
+    if (bk == 32 && cl == 1 && k > 1) {
+        // k-tap conv / data gradient: tap-reuse kernel, 64-column tiles when 128-column ones cannot fill the machine
+        const bool n64 = narrow && !((long long)t_tiles * ((Nc + 127) / 128) * B > 148);
+        const bool ok = n64 ? taps_usable<1, 64>(k, p.tap_off, (long long)t_tiles * (Nc / 64) * B)
+                            : taps_usable<1, 128>(k, p.tap_off, (long long)t_tiles * (Nc / 128) * B);
+        if (ok) {
+            const TapGeom g = n64 ? tap_geom<1, 64>(k, p.tap_off) : tap_geom<1, 128>(k, p.tap_off);
+            for (int pl = 0; pl < 2; ++pl) {
+                if (encode_tmap_bf16_3d(&maps.a[pl], plane(a, pl, (long long)B * T * Kp), Kc, T, B, (uint64_t)Kp * 2,
+                                        (uint64_t)T * Kp * 2, bk, g.a_rows)) return 1;
+                if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
+                                        (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, n64 ? 64 : 128)) return 1;
+            }
+            if (n64) return launch_tc_taps<TC_CONV, 1, 64>(maps, p, g, t_tiles, Nc / 64, B, st, "tc_conv(taps64)");
+            return launch_tc_taps<TC_CONV, 1, 128>(maps, p, g, t_tiles, Nc / 128, B, st, "tc_conv(taps)");
+        }
+    }
     if (tc_persist() && bk == 32 && cl == 1 && (long long)t_tiles * ((Nc + 127) / 128) * B > 148) {
         // more 128-column tiles than SMs: persistent kernel with double-buffered accumulators
         if (br != 128) {

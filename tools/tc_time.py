@@ -10,7 +10,7 @@ from deepvoice3_pytorch_b200 import ops  # noqa: E402
 
 ops.conv_math = "tc"
 dev = "cuda"
-for (B, C, T, k, d) in [(16, 512, 800, 3, 1), (16, 256, 800, 3, 3), (16, 512, 128, 3, 9), (16, 256, 200, 3, 9)]:
+for (B, C, T, k, d) in [(16, 512, 800, 3, 1), (16, 512, 800, 3, 27), (16, 256, 800, 3, 3), (16, 512, 128, 3, 9), (16, 256, 200, 3, 9)]:
     v = (torch.randn(2 * C, C, k, device=dev) * (4.0 / (k * C)) ** 0.5).requires_grad_(True)
     g = v.detach().pow(2).sum((1, 2), keepdim=True).sqrt().requires_grad_(True)
     bias = torch.zeros(2 * C, device=dev, requires_grad=True)
@@ -25,6 +25,8 @@ for (B, C, T, k, d) in [(16, 512, 800, 3, 1), (16, 256, 800, 3, 3), (16, 512, 12
     for e in prof.key_averages():
         if "tc_conv_kernel" in e.key:
             rows[e.key.split("tc_conv_kernel")[1][:18]] = e.device_time_total / e.count
+        elif "tc_conv_taps" in e.key:
+            rows["taps" + e.key.split("tc_conv_taps_kernel")[1][:10]] = e.device_time_total / e.count
         elif "tc_conv_persist" in e.key:
             rows["persist" + e.key.split("tc_conv_persist_kernel")[1][:10]] = e.device_time_total / e.count
         elif "tc_wgrad_mn" in e.key or "wn_bwd" in e.key:
