@@ -6,23 +6,9 @@
 // the TMA stride granularity); pad columns are never read (the tensor maps carry the true extent).
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "wn_device.cuh"
 
 namespace dv3 {
-
-typedef __nv_bfloat16 bf16;
-
-template <int NPL>
-__device__ __forceinline__ void split_store(float v, bf16* __restrict__ base, size_t idx, size_t plane_stride) {
-    const bf16 h = __float2bfloat16_rn(v);
-    base[idx] = h;
-    float r = v - __bfloat162float(h);
-    const bf16 m = __float2bfloat16_rn(r);
-    base[plane_stride + idx] = m;
-    if (NPL == 3) {
-        r -= __bfloat162float(m);
-        base[2 * plane_stride + idx] = __float2bfloat16_rn(r);
-    }
-}
 
 struct TapList { int k; int off[8]; };
 
@@ -153,42 +139,13 @@ __global__ void wn_pack_split_kernel(const float* __restrict__ v, const float* _
                                      long long a_plane, bf16* __restrict__ outB, long long b_r, long long b_x,
                                      long long b_j, long long b_plane, int R, int X, int k) {
     __shared__ float tile[32][33];
-    const int L = X * k;
-    const int r0 = blockIdx.y * 32, e0 = blockIdx.x * 32;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = r0 + threadIdx.y + 8 * i, e = e0 + threadIdx.x;
-        float w = 0.f;
-        if (r < R && e < L) {
-            w = v[(size_t)r * L + e] * scale[r];
-            const int xx = e / k, j = e - xx * k;
-            if (outA) split_store<NPLA>(w, outA, (size_t)(r * a_r + xx * a_x + j * a_j), (size_t)a_plane);
-        }
-        tile[threadIdx.y + 8 * i][threadIdx.x] = w;
-    }
-    __syncthreads();
-    if (outB) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int e = e0 + threadIdx.y + 8 * i, r = r0 + threadIdx.x;
-            if (r < R && e < L) {
-                const int xx = e / k, j = e - xx * k;
-                split_store<NPLB>(tile[threadIdx.x][threadIdx.y + 8 * i], outB,
-                                  (size_t)(r * b_r + xx * b_x + j * b_j), (size_t)b_plane);
-            }
-        }
-    }
+    wn_pack_split_tile<NPLA, NPLB>(v, scale, outA, a_r, a_x, a_j, a_plane, outB, b_r, b_x, b_j, b_plane, R, X, k,
+                                   blockIdx.x, blockIdx.y, tile);
 }
 
 __global__ void wn_norm_kernel2(const float* __restrict__ v, const float* __restrict__ g,
                                 float* __restrict__ inv_norm, float* __restrict__ scale, int R, int L) {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (r >= R) return;
-    const float* row = v + (size_t)r * L;
-    float s = 0.f;
-    for (int e = lane; e < L; e += 32) { const float xx = row[e]; s = fmaf(xx, xx, s); }
-    s = warp_sum(s);
-    if (lane == 0) { const float inv = 1.f / sqrtf(s); inv_norm[r] = inv; scale[r] = g[r] * inv; }
+    wn_norm_row(v, g, inv_norm, scale, R, L, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31);
 }
 
 }  // namespace dv3

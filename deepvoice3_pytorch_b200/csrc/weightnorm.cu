@@ -4,6 +4,7 @@
 // (forward operand and data-gradient operand) so no separate transpose/pack pass exists;
 // the backward folds the split-K reduction of the weight-gradient partials into the g/v gradient.
 #include "common.cuh"
+#include "wn_device.cuh"
 
 namespace dv3 {
 
@@ -55,70 +56,13 @@ __global__ void wn_pack_kernel(const float* __restrict__ v, const float* __restr
     }
 }
 
-// backward, one CTA (256 threads) per row:  dW = sum_s partial[s] ;  dot = <dW, v>
-//   dg = dot * inv_norm ;  dv = scale*dW - scale*dot*inv_norm^2 * v
-// (one warp per row left the big layers -- 1024 rows x 1536 x up to 16 partials -- at 0.4 TB/s.)
-// Partials are either in v's own layout (jmajor_X == 0: element e of row r at r*L + e) or tap-major
-// (jmajor_X = X > 0: element (r, x, j) at (j*R + r)*X + x -- what the tensor-core weight-gradient kernel writes with
-// contiguous float4 stores).  The reduced dW is parked in partial slot 0 between the two passes, so dv / dg can be
-// ACCUMULATED into (accumulate = 1: the flat gradient arena of the training step, no autograd add kernel afterwards).
+// backward, one CTA (256 threads) per row (body in wn_device.cuh)
 __global__ void __launch_bounds__(256) wn_bwd_kernel(float* __restrict__ dw_partials, long long split_stride,
                                                      int nsplit, int jmajor_X, const float* __restrict__ v,
                                                      const float* __restrict__ g,
                                                      const float* __restrict__ inv_norm, float* __restrict__ dv,
                                                      float* __restrict__ dg, int R, int L, int accumulate) {
-    __shared__ float red[8];
-    __shared__ float s_dot;
-    const int r = blockIdx.x, tid = threadIdx.x;
-    const size_t base = (size_t)r * L;
-    const int X = jmajor_X > 0 ? jmajor_X : L, k = L / X;
-    float dot = 0.f;
-    const bool vec4 = jmajor_X > 0 && (X & 3) == 0 && (split_stride & 3) == 0;
-    if (vec4) {                                          // tap-major partials: float4 along x, v gathered at stride k
-        const int X4 = X >> 2;
-        for (int q = tid; q < k * X4; q += 256) {
-            const int j = q / X4, x = (q - j * X4) << 2;
-            const size_t po = ((size_t)j * R + r) * X + x;
-            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s = 0; s < nsplit; ++s) {
-                const float4 t = *reinterpret_cast<const float4*>(&dw_partials[(size_t)s * split_stride + po]);
-                d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
-            }
-            *reinterpret_cast<float4*>(&dw_partials[po]) = d;
-            const float* vv = v + base + (size_t)x * k + j;
-            dot = fmaf(d.x, vv[0], dot); dot = fmaf(d.y, vv[k], dot);
-            dot = fmaf(d.z, vv[2 * k], dot); dot = fmaf(d.w, vv[3 * k], dot);
-        }
-    } else {
-        for (int q = tid; q < L; q += 256) {             // q runs over the partial's own (coalesced) order
-            size_t po; int e;
-            if (jmajor_X > 0) { const int j = q / X, x = q - j * X; e = x * k + j; po = ((size_t)j * R + r) * X + x; }
-            else { e = q; po = base + q; }
-            float d = 0.f;
-            for (int s = 0; s < nsplit; ++s) d += dw_partials[(size_t)s * split_stride + po];
-            dw_partials[po] = d;
-            dot = fmaf(d, v[base + e], dot);
-        }
-    }
-    dot = warp_sum(dot);
-    if ((tid & 31) == 0) red[tid >> 5] = dot;
-    __syncthreads();
-    if (tid < 32) {
-        float t = tid < 8 ? red[tid] : 0.f;
-        t = warp_sum(t);
-        if (tid == 0) s_dot = t;
-    }
-    __syncthreads();
-    dot = s_dot;
-    const float inv = inv_norm[r], sc = g[r] * inv, c2 = sc * dot * inv * inv;
-    for (int q = tid; q < L; q += 256) {                 // same thread -> same elements as in the first pass
-        size_t po; int e;
-        if (jmajor_X > 0) { const int j = q / X, x = q - j * X; e = x * k + j; po = ((size_t)j * R + r) * X + x; }
-        else { e = q; po = base + q; }
-        const float val = sc * dw_partials[po] - c2 * v[base + e];
-        dv[base + e] = accumulate ? dv[base + e] + val : val;
-    }
-    if (tid == 0) dg[r] = accumulate ? dg[r] + dot * inv : dot * inv;
+    wn_bwd_row(dw_partials, split_stride, nsplit, jmajor_X, v, g, inv_norm, dv, dg, R, L, accumulate, blockIdx.x);
 }
 
 }  // namespace dv3

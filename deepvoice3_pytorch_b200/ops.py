@@ -114,6 +114,16 @@ def _wn_conv_fwd(v, g):
 grad_sink = False
 
 
+# Batched weight norm (weight_bank.WeightBank), installed by train_step.TrainStep for the duration of one
+# forward/backward: operand planes of every layer are prepared up front, the weight-norm backward is deferred to one
+# launch after loss.backward().  None: every Function normalises / reduces its own layer.
+weight_bank = None
+
+
+def _bank_weights(v, g):
+    return weight_bank.weights_for(v, g) if weight_bank is not None else None
+
+
 def _sink(*params):
     """The .grad buffers to accumulate into, or None when the sink is off / not every buffer exists."""
     if not grad_sink or any(p.grad is None or not p.grad.is_contiguous() for p in params):
@@ -258,23 +268,31 @@ class _ConvBlockTCFn(torch.autograd.Function):
         bf = torch.bfloat16
         npl = _fwd_planes()
         need_bwd = any(ctx.needs_input_grad)
-        inv = torch.empty(2 * C, device=dev)
-        scale = torch.empty_like(inv)
-        wfwd = torch.empty(npl, k, 2 * C, C, device=dev, dtype=bf)
-        wbwd = torch.empty(2, k, C, 2 * C, device=dev, dtype=bf)
+        bank = _bank_weights(v, g)        # operand planes already prepared for the whole model this step?
+        if bank is not None:
+            inv, wfwd, wbwd = bank.inv, bank.wfwd, bank.wbwd
+        else:
+            inv = torch.empty(2 * C, device=dev)
+            scale = torch.empty_like(inv)
+            wfwd = torch.empty(npl, k, 2 * C, C, device=dev, dtype=bf)
+            wbwd = torch.empty(2, k, C, 2 * C, device=dev, dtype=bf)
         p, seed_ptr, salt = _drop_args(p_drop, training, dev)
         x_btc = torch.empty(npl, B, T, C, device=dev, dtype=bf)
         x_bct = torch.empty(2, k, B, C, T, device=dev, dtype=bf) if (need_bwd and not wgrad_mn) else None
         y = torch.empty_like(x)
         a = torch.empty_like(x) if need_bwd else None
         s = torch.empty_like(x) if need_bwd else None
-        side = _SideStream(dev)
-        with side:                        # weight norm + split depends only on the parameters: overlap it with
-            lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), npl, _p(wbwd), 2 * C, C, k,
-                     _stream())           # the activation split below
-        lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, C, T, k, dilation, int(causal), p,
-                 seed_ptr, salt, _stream())
-        side.join()
+        if bank is not None:
+            lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, C, T, k, dilation, int(causal), p,
+                     seed_ptr, salt, _stream())
+        else:
+            side = _SideStream(dev)
+            with side:                    # weight norm + split depends only on the parameters: overlap it with
+                lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), npl, _p(wbwd), 2 * C, C,
+                         k, _stream())    # the activation split below
+            lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, C, T, k, dilation, int(causal), p,
+                     seed_ptr, salt, _stream())
+            side.join()
         if need_bwd and wgrad_mn:
             x_bct = x_btc                 # the weight gradient reads the forward's own planes
         lib.call("dv3_tc_convblock_fwd", _p(x_btc), _p(wfwd), npl, _p(bias), _p(spk), _p(x), _p(y), _p(a), _p(s),
@@ -283,6 +301,7 @@ class _ConvBlockTCFn(torch.autograd.Function):
             ctx.save_for_backward(x, v, g, a, s, x_bct, wbwd, inv)
             ctx.cfg = (k, dilation, causal, mode, residual, p, salt, spk is not None, dev)
             ctx.bias_param = bias if bias.is_leaf else None
+            ctx.bank = bank
         return y
 
     @staticmethod
@@ -304,7 +323,12 @@ class _ConvBlockTCFn(torch.autograd.Function):
         if need_w:                                   # allocate on the main stream, compute on the side stream
             nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, 2 * C, C, T, k)
             numel = v.numel()
-            partials = torch.empty(nsplit, numel, device=dev)
+            # with the weight bank the split-K partials go to the layer's persistent buffer and the weight-norm
+            # backward of ALL layers runs as one launch after loss.backward() (WeightBank.end_backward)
+            partials = weight_bank.partials_for(ctx.bank, nsplit, numel) if (sink and ctx.bank is not None) else None
+            deferred = partials is not None
+            if not deferred:
+                partials = torch.empty(nsplit, numel, device=dev)
             dv, dg = (sink[0], sink[1]) if sink else (torch.empty_like(v), torch.empty_like(g))
         side = _SideStream(dev)
         if need_w:
@@ -316,7 +340,8 @@ class _ConvBlockTCFn(torch.autograd.Function):
                 else:
                     lib.call("dv3_tc_wgrad", _p(d_bct), _p(x_bct), _p(partials), numel, B, 2 * C, C, T, k, 2 * C, C, 0,
                              1, 2 * C * C, _stream())
-                _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k, out=(dv, dg), accumulate=bool(sink))
+                if not deferred:
+                    _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k, out=(dv, dg), accumulate=bool(sink))
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
@@ -351,21 +376,29 @@ class _Conv1dTCFn(torch.autograd.Function):
         npl = _fwd_planes()
         need_bwd = any(ctx.needs_input_grad)
         Cinp, Coutp = _pad8(Cin), _pad8(Cout)
-        inv = torch.empty(Cout, device=dev)
-        scale = torch.empty_like(inv)
-        wfwd = torch.empty(npl, k, Cout, Cinp, device=dev, dtype=bf)
-        wbwd = torch.empty(2, k, Cin, Coutp, device=dev, dtype=bf)
+        bank = _bank_weights(v, g)
+        if bank is not None:
+            inv, wfwd, wbwd = bank.inv, bank.wfwd, bank.wbwd
+        else:
+            inv = torch.empty(Cout, device=dev)
+            scale = torch.empty_like(inv)
+            wfwd = torch.empty(npl, k, Cout, Cinp, device=dev, dtype=bf)
+            wbwd = torch.empty(2, k, Cin, Coutp, device=dev, dtype=bf)
         x_btc = torch.empty(npl, B, T, Cinp, device=dev, dtype=bf)
         need_w = need_bwd and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         x_bct = torch.empty(2, k, B, Cin, T, device=dev, dtype=bf) if (need_w and not wgrad_mn) else None
         y = torch.empty(B, Cout, T, device=dev)
-        side = _SideStream(dev)
-        with side:
-            lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), npl, _p(wbwd), Cout, Cin, k,
-                     _stream())
-        lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, Cin, T, k, dilation, int(causal), 0.0,
-                 None, 0, _stream())
-        side.join()
+        if bank is not None:
+            lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, Cin, T, k, dilation, int(causal), 0.0,
+                     None, 0, _stream())
+        else:
+            side = _SideStream(dev)
+            with side:
+                lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), npl, _p(wbwd), Cout, Cin,
+                         k, _stream())
+            lib.call("dv3_tc_split_input", _p(x), _p(x_btc), npl, _p(x_bct), B, Cin, T, k, dilation, int(causal), 0.0,
+                     None, 0, _stream())
+            side.join()
         if need_w and wgrad_mn:
             x_bct = x_btc
         lib.call("dv3_tc_conv", _p(x_btc), _p(wfwd), npl, _p(y), B, Cin, Cout, T, k, dilation, int(causal), 0,
@@ -374,6 +407,7 @@ class _Conv1dTCFn(torch.autograd.Function):
             ctx.save_for_backward(v, g, x_bct, wbwd, inv, y if relu else None)
             ctx.cfg = (B, Cin, Cout, T, k, dilation, causal, relu)
             ctx.bias_param = bias if bias.is_leaf else None
+            ctx.bank = bank
         return y
 
     @staticmethod
@@ -395,7 +429,10 @@ class _Conv1dTCFn(torch.autograd.Function):
         if need_w:
             nsplit = lib.raw("dv3_tc_wgrad_nsplit")(B, Cout, Cin, T, k)
             numel = v.numel()
-            partials = torch.empty(nsplit, numel, device=dev)
+            partials = weight_bank.partials_for(ctx.bank, nsplit, numel) if (sink and ctx.bank is not None) else None
+            deferred = partials is not None
+            if not deferred:
+                partials = torch.empty(nsplit, numel, device=dev)
             dv, dg = (sink[0], sink[1]) if sink else (torch.empty_like(v), torch.empty_like(g))
             with side:
                 if wgrad_mn:
@@ -404,7 +441,8 @@ class _Conv1dTCFn(torch.autograd.Function):
                 else:
                     lib.call("dv3_tc_wgrad", _p(g_bct), _p(x_bct), _p(partials), numel, B, Cout, Cin, T, k, Cout, Cin,
                              0, 1, Cout * Cin, _stream())
-                _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k, out=(dv, dg), accumulate=bool(sink))
+                if not deferred:
+                    _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k, out=(dv, dg), accumulate=bool(sink))
         dx = None
         if need_x:
             dx = torch.empty(B, Cin, T, device=dev)

@@ -15,6 +15,7 @@ backward, ``clip_grad_norm_``, ``Adam.step`` -- restated around three ideas:
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -23,6 +24,7 @@ import torch.nn.functional as F
 
 from . import ops
 from ._lib import lib
+from .weight_bank import WeightBank
 
 
 def noam_learning_rate_decay(init_lr, global_step, warmup_steps=4000):
@@ -223,7 +225,7 @@ class TrainStep:
     def __init__(self, model, init_lr=5e-4, betas=(0.5, 0.9), eps=1e-6, clip_thresh=0.1, r=1, downsample_step=4,
                  masked_loss_weight=0.5, binary_divergence_weight=0.1, guided_attention_sigma=0.2,
                  use_guided_attention=True, lr_schedule=noam_learning_rate_decay, use_graph=False,
-                 fused_loss=True):
+                 fused_loss=True, weight_bank=None):
         self.model = model
         self.arena = ParameterArena(model)
         self.opt = FlatAdam(self.arena, init_lr, betas, eps, clip_thresh)
@@ -240,15 +242,24 @@ class TrainStep:
         self._static = None
         self._loss = None
         self.launches_per_step = None       # dv3 kernel launches inside one captured step (graph mode)
+        if weight_bank is None:
+            weight_bank = os.environ.get("DV3_WEIGHT_BANK", "1") == "1"
+        self.bank = WeightBank() if weight_bank else None
 
     # -- pieces -------------------------------------------------------------------------------
     def _forward_backward(self, batch):
         self.arena.zero_grad()
         ops.grad_sink = True          # kernels accumulate parameter gradients straight into the arena
+        ops.weight_bank = self.bank   # weight norm of all layers: 2 launches up front, 1 after the backward pass
         try:
+            if self.bank is not None:
+                self.bank.begin_step()
             return self._forward_backward_inner(batch)
         finally:
             ops.grad_sink = False
+            ops.weight_bank = None
+            if self.bank is not None:
+                self.bank.end_step()
 
     def _forward_backward_inner(self, batch):
         outs = self.model(batch["x"], batch["mel"], speaker_ids=batch.get("speaker_ids"),
@@ -256,6 +267,8 @@ class TrainStep:
                           input_lengths=batch["input_lengths_dev"])
         loss = self.loss_fn(outs, batch, **self.loss_kw)
         loss.backward()
+        if self.bank is not None:
+            self.bank.end_backward()
         return loss.detach()
 
     def _exchange_and_update(self):

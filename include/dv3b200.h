@@ -167,6 +167,23 @@ int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float
  * wfwd: [npl][2*Cout][Cinp], wbwd: [2][Cin][pad8(2*Cout)]. */
 int dv3_tc_weightnorm_convt_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wfwd, int npl,
                                 void* wbwd, int Cin, int Cout, void* stream);
+/* Batched weight norm (csrc/wn_batched.cu): one record per weight-normed conv (v (Cout,Cin,k), g [Cout]); the table
+ * lives in DEVICE memory, blk_* are the first block of the record in the batched norm / pack / backward launches
+ * (ascending over the table), pack_gx = ceil(Cin*k / 32).  Layouts as dv3_tc_weightnorm_fwd with npl = 2; the
+ * backward consumes tap-major partials [nsplit][k][Cout][Cin] (what dv3_tc_wgrad_mn writes; slot 0 is scratch). */
+typedef struct Dv3WnEntry {
+    const float* v; const float* g; float* inv_norm; float* scale;
+    void* wfwd; void* wbwd;
+    float* partials; float* dv; float* dg;
+    long long split_stride;
+    int Cout, Cin, k, nsplit;
+    int blk_norm, blk_pack, blk_bwd, pack_gx;
+} Dv3WnEntry;
+/* norm + pack of every record: 2 launches (replaces 2 launches per layer). */
+int dv3_tc_weightnorm_fwd_batched(const Dv3WnEntry* table_dev, int n, int norm_blocks, int pack_blocks,
+                                  void* stream);
+/* split-K reduction + dg / dv of every record: 1 launch; accumulate = 1 adds into dv / dg. */
+int dv3_weightnorm_bwd_batched(const Dv3WnEntry* table_dev, int n, int bwd_blocks, int accumulate, void* stream);
 /* gated forward: xd = btc planes of dv3_tc_split_input, w = wfwd planes [npl][k][2C][C]. */
 int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bias, const float* spk,
                          const float* res, float* y, float* save_a, float* save_s, int B, int C, int T, int k,

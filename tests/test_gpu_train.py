@@ -129,3 +129,50 @@ def test_gradient_sink_equals_autograd():
             torch.testing.assert_close(g_sink, g_autograd, rtol=1e-5, atol=1e-7)
     finally:
         ops.conv_math = old_math
+
+
+@pytest.mark.gpu
+def test_weight_bank_equals_per_layer_weight_norm():
+    """The batched weight norm of TrainStep (WeightBank: all layers normalised / packed in two launches, all weight-norm
+    backwards in one) does the same arithmetic as the per-layer kernels: same gradients (up to the atomics noise of
+    the embedding / bias reductions), same losses over optimizer steps in eager and CUDA-graph mode, and the bank
+    really is in use from the second pass on."""
+    from deepvoice3_pytorch_b200 import builder, ops
+    from deepvoice3_pytorch_b200.train_step import TrainStep, make_synthetic_batch, to_device
+    kw = dict(n_vocab=149, embed_dim=64, mel_dim=80, linear_dim=129, r=1, downsample_step=4, kernel_size=3,
+              encoder_channels=128, decoder_channels=128, converter_channels=128, use_memory_mask=True,
+              key_projection=True, value_projection=True, dropout=0.05, max_positions=256)
+    dev = to_device(make_synthetic_batch(B=2, T_text=24, T_mel=64, linear_dim=129, seed=9), "cuda")
+    old_math = ops.conv_math
+    ops.conv_math = "tc"
+    try:
+        def make(bank, graph):
+            torch.manual_seed(0)
+            ops.rng.manual_seed(77, torch.device("cuda"))
+            return TrainStep(builder.deepvoice3(**kw).cuda().train(), use_graph=graph, weight_bank=bank)
+
+        def grads(bank):
+            step = make(bank, False)
+            step._forward_backward(dev)              # first pass registers the layers (per-layer kernels)
+            loss = step._forward_backward(dev)       # second pass: prepared planes + deferred weight-norm backward
+            torch.cuda.synchronize()
+            return step, float(loss), step.arena.grad.clone()
+
+        _, l_ref, g_ref = grads(False)
+        step, l_bank, g_bank = grads(True)
+        assert len(step.bank.layers) > 10 and step.bank._fwd is not None and step.bank._bwd is not None
+        assert float(g_ref.abs().max()) > 0
+        assert abs(l_bank - l_ref) <= 1e-6 * abs(l_ref)
+        torch.testing.assert_close(g_bank, g_ref, rtol=1e-5, atol=1e-7)
+
+        def losses(bank, graph):
+            step = make(bank, graph)
+            out = [float(step.step(dev)) for _ in range(4)]
+            torch.cuda.synchronize()
+            return out
+
+        ref = losses(False, False)
+        for graph in (False, True):
+            np.testing.assert_allclose(losses(True, graph), ref, rtol=2e-5)
+    finally:
+        ops.conv_math = old_math
