@@ -11,6 +11,8 @@ from deepvoice3_pytorch_b200 import ops  # noqa: E402
 
 ops.conv_math = sys.argv[1] if len(sys.argv) > 1 else "tc"
 B, C, T, k, d = 16, 512, 800, 3, 1
+if len(sys.argv) > 6:
+    B, C, T, k, d = [int(a) for a in sys.argv[2:7]]
 dev = "cuda"
 v = (torch.randn(2 * C, C, k, device=dev) * (4.0 / (k * C)) ** 0.5).requires_grad_(True)
 g = v.detach().pow(2).sum((1, 2), keepdim=True).sqrt().requires_grad_(True)
