@@ -55,11 +55,19 @@ class Conv1d(_WeightNormed):
                           causal=causal, relu=relu)
 
     def incremental_forward(self, input):
-        raise NotImplementedError("incremental (inference) decoding is outside the training hot path "
-                                  "(SURVEY.md section 8f.3)")
+        """input (B, T, Cin): the newest frame input[:, -1] enters the ring buffer of the last (k-1)*dilation+1
+        frames -> (B, 1, Cout) (reference conv.py:17-46).  Eval mode only; ``clear_buffer`` starts a new sequence
+        (and re-folds the weight norm)."""
+        if self.training:
+            raise RuntimeError("incremental_forward only supports eval mode")
+        from .incremental import ModuleStepper
+        st = self.__dict__.get("_stepper")
+        if st is None or st.B != input.size(0):
+            st = self.__dict__["_stepper"] = ModuleStepper(self, input.size(0))
+        return st.step(input[:, -1, :])
 
     def clear_buffer(self):
-        pass
+        self.__dict__.pop("_stepper", None)
 
     def extra_repr(self):
         return "%d, %d, kernel_size=%d, dilation=%d, padding=%d" % (

@@ -116,7 +116,8 @@ class AttentionLayer(nn.Module):
     def forward(self, query, encoder_out, mask=None, last_attended=None):
         """Reference signature: query (B,Td,C); encoder_out = (keys (B,E,Ts) pre-transposed, values (B,Ts,E))."""
         if last_attended is not None:
-            raise NotImplementedError("attention windowing belongs to incremental decoding (out of the hot path)")
+            raise NotImplementedError("the attention window (last_attended) is applied by the incremental step kernel "
+                                      "(incremental.py); the batch forward has no windowed mode")
         keys, values = encoder_out
         x, probs = self.forward_bct(ops.transpose12(query), keys, ops.transpose12(values), mask)
         return ops.transpose12(x), probs
@@ -183,9 +184,10 @@ class Decoder(nn.Module):
                 lengths=None):
         """Teacher-forced decoder (reference deepvoice3.py:277-365).
         -> outputs (B,T,in_dim*r), alignments (N_attn,B,T,T_text), done (B,T,1), decoder_states (B,T,C)."""
-        if inputs is None:
-            raise NotImplementedError("autoregressive incremental_forward is outside the training hot path "
-                                      "(SURVEY.md section 8f.3)")
+        if inputs is None:                 # inference: autoregressive decoding (reference deepvoice3.py:280-284)
+            assert text_positions is not None
+            self.start_fresh_sequence()
+            return self.incremental_forward(encoder_out, text_positions, speaker_embed)
         if inputs.size(-1) == self.in_dim:
             inputs = inputs.reshape(inputs.size(0), inputs.size(1) // self.r, -1)
         assert inputs.size(-1) == self.in_dim * self.r
@@ -230,11 +232,19 @@ class Decoder(nn.Module):
         done = torch.sigmoid(self.fc(x))
         return outputs, torch.stack(alignments), done, decoder_states
 
-    def incremental_forward(self, *args, **kwargs):
-        raise NotImplementedError("autoregressive decoding is outside the training hot path")
+    def incremental_forward(self, encoder_out, text_positions, speaker_embed=None, initial_input=None,
+                            test_inputs=None):
+        """Autoregressive decoding (reference deepvoice3.py:367-485) as a CUDA-graph-replayed step program;
+        see incremental.py.  -> outputs (B,N,in_dim*r), alignments (B,N,T_text), dones [N x (B,1,1)], states."""
+        from .incremental import decode
+        return decode(self, encoder_out, text_positions, speaker_embed, initial_input, test_inputs)
 
     def start_fresh_sequence(self):
-        pass
+        """All step state (ring buffers, cursors) is created per incremental_forward call; only the module-level
+        steppers need clearing (reference deepvoice3.py:487-490)."""
+        for m in list(self.preattention) + list(self.convolutions) + [self.last_conv]:
+            if hasattr(m, "clear_buffer"):
+                m.clear_buffer()
 
 
 class Converter(nn.Module):

@@ -113,11 +113,19 @@ class _GatedConv(nn.Module):
         self.conv = Conv1d(in_channels, 2 * out_channels, kernel_size, dropout=dropout, padding=padding,
                            dilation=dilation, std_mul=std_mul)
 
-    def incremental_forward(self, *a, **k):
-        raise NotImplementedError("incremental (inference) decoding is outside the training hot path")
+    def _step(self, x, mode, spk=None, residual=False):
+        """One autoregressive step of the block on x (B, T, C) (newest frame = x[:, -1]) -> (B, 1, C)."""
+        if self.training:
+            raise RuntimeError("incremental_forward only supports eval mode")
+        from .incremental import ModuleStepper
+        st = self.__dict__.get("_stepper")
+        if st is None or st.B != x.size(0):
+            st = self.__dict__["_stepper"] = ModuleStepper(self.conv, x.size(0), mode=mode, spk=spk,
+                                                           residual=residual)
+        return st.step(x[:, -1, :])
 
     def clear_buffer(self):
-        pass
+        self.__dict__.pop("_stepper", None)
 
 
 class Conv1dGLU(_GatedConv):
@@ -145,6 +153,15 @@ class Conv1dGLU(_GatedConv):
                              self.causal, ops.MODE_GLU, residual, self.dropout, self.training)
 
 
+    def incremental_forward(self, x, speaker_embed=None):
+        """reference modules.py:142-143: x (B, 1, C); speaker_embed (B, S) -- constant over the sequence, so its
+        softsign projection is computed when the step state is created (clear_buffer resets it)."""
+        spk = None
+        if self.speaker_proj is not None and "_stepper" not in self.__dict__:
+            spk = F.softsign(self.speaker_proj(speaker_embed.reshape(x.size(0), -1)))
+        return self._step(x, 1, spk=spk, residual=self.residual)
+
+
 class HighwayConv1d(_GatedConv):
     """Weight-normalized Conv1d + highway gate -- reference modules.py:170-229 (glu=False branch)."""
 
@@ -162,6 +179,10 @@ class HighwayConv1d(_GatedConv):
         c = self.conv
         return ops.convblock(x, c.weight_v, c.weight_g, c.bias, None, c.kernel_size[0], c.dilation[0],
                              self.causal, ops.MODE_HIGHWAY, True, self.dropout, self.training)
+
+    def incremental_forward(self, x):
+        """reference modules.py:197-198."""
+        return self._step(x, 2)
 
 
 def get_mask_from_lengths(memory, memory_lengths):

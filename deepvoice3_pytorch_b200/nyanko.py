@@ -79,8 +79,10 @@ class Decoder(nn.Module):
     def forward(self, encoder_out, inputs=None, text_positions=None, frame_positions=None, speaker_embed=None,
                 lengths=None):
         """Teacher-forced decoder (reference nyanko.py:177-248)."""
-        if inputs is None:
-            raise NotImplementedError("autoregressive incremental_forward is outside the training hot path")
+        if inputs is None:                 # inference (reference nyanko.py:180-184)
+            assert text_positions is not None
+            self.start_fresh_sequence()
+            return self.incremental_forward(encoder_out, text_positions)
         if inputs.size(-1) == self.in_dim:
             inputs = inputs.reshape(inputs.size(0), inputs.size(1) // self.r, -1)
         assert inputs.size(-1) == self.in_dim * self.r
@@ -102,11 +104,15 @@ class Decoder(nn.Module):
         done = torch.sigmoid(self.fc(x))
         return outputs, alignments.unsqueeze(0), done, decoder_states
 
-    def incremental_forward(self, *args, **kwargs):
-        raise NotImplementedError("autoregressive decoding is outside the training hot path")
+    def incremental_forward(self, encoder_out, text_positions, initial_input=None, test_inputs=None):
+        """Autoregressive decoding (reference nyanko.py:250-338); see incremental.py."""
+        from .incremental import decode
+        return decode(self, encoder_out, text_positions, None, initial_input, test_inputs)
 
     def start_fresh_sequence(self):
-        pass
+        for m in list(self.audio_encoder_modules) + list(self.audio_decoder_modules) + [self.last_conv]:
+            if hasattr(m, "clear_buffer"):
+                m.clear_buffer()
 
 
 class Converter(nn.Module):

@@ -60,7 +60,10 @@ class MultiSpeakerTTSModel(nn.Module):
         return (p for p in self.parameters() if id(p) not in skip)
 
     def make_generation_fast_(self):
-        raise NotImplementedError("weight-norm folding for inference is outside the training hot path")
+        """The reference strips the weight-norm hooks here so inference stops re-normalising every call
+        (__init__.py:39-46).  Nothing to strip in this implementation: the incremental decoder folds g*v/||v|| once
+        per utterance (incremental.py) and the parameters keep their reference names."""
+        return None
 
     # -- forward ------------------------------------------------------------------------------------------
     def _speaker_embedding(self, speaker_ids):

@@ -216,6 +216,42 @@ int dv3_aux_loss(const float* done_hat, const float* done, float* d_done, long l
                  float* d_attn, const long long* in_len, const long long* dec_len, int A, int B, int Td, int Ts,
                  float sigma, int use_attn, float* loss, void* stream);
 
+/* ---- incremental (autoregressive) decoding: reference conv.py:17-46, deepvoice3.py:367-485, nyanko.py:250-338 ----
+ * All loop state lives in device memory so that one decoder step is the same launch sequence every time (CUDA-graph
+ * replay): *t_ptr is the step counter; every row pointer advances by a per-step stride: row b of step t of operand
+ * X is X + b*X_ld + t*X_t (floats). */
+typedef struct Dv3IncStep {
+    const float* x; long long x_ld, x_t;          /* current input (B, Cin) */
+    const float* add; long long add_ld, add_t;    /* optional, added to the input (position encoding) */
+    float* ring;                                   /* (B, (k-1)*dilation+1, Cin) zero-initialised history; NULL: k = 1 */
+    const float* w; const float* bias;             /* normalised weight linearised as [Cout][k][Cin]; [Cout] */
+    const float* spk; long long spk_ld;            /* GLU: softsign(speaker_proj(embed)) (B, C) or NULL */
+    const float* res1; long long res1_ld, res1_t;  /* y = (y + res1)*sqrt(.5) if non-NULL, then the same with res2 */
+    const float* res2; long long res2_ld, res2_t;
+    float* y; long long y_ld, y_t;
+    float* y2; long long y2_ld, y2_t;              /* optional second output, see y2_mode */
+    const float* yadd; long long yadd_ld, yadd_t;  /* y2_mode 2: y2 = y + yadd (position encoding of the query) */
+    const int* t_ptr;
+    int B, Cin, Cout, k, dilation;
+    int mode;                                      /* 0 plain conv, 1 GLU (a*sigmoid(b)), 2 highway */
+    int act;                                       /* plain: 0 none, 1 ReLU, 2 sigmoid */
+    int vec4;                                      /* 1: Cin % 4 == 0 and every input row is 16-byte aligned */
+    int y2_mode;                                   /* 1: y2 = sigmoid(y); 2: y2 = y + yadd */
+} Dv3IncStep;
+int dv3_inc_conv_step(const Dv3IncStep* step, void* stream);
+typedef struct Dv3IncAttn {
+    const float* q; long long q_ld;                /* projected query (B, E) */
+    const float* keys; const float* values;        /* (B, E, Ts) pre-transposed, (B, Ts, E): projected once */
+    float* ctx; long long ctx_ld;                  /* context * Ts*sqrt(1/Ts) (B, E) */
+    float* align; long long align_ld, align_t;     /* probabilities * align_scale, or NULL */
+    int* last_attended;                            /* int[2] (slot t&1 read, (t+1)&1 written) or NULL: no window */
+    const int* t_ptr;
+    float align_scale;
+    int B, E, Ts, window_backward, window_ahead;
+} Dv3IncAttn;
+int dv3_inc_attn_step(const Dv3IncAttn* attn, void* stream);
+int dv3_inc_advance(int* t_ptr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

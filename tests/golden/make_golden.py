@@ -249,6 +249,87 @@ def model_cases():
     fx.save("models.npz")
 
 
+def incremental_cases():
+    """Inference path: Decoder.incremental_forward (reference deepvoice3.py:367-485, nyanko.py:250-338) teacher-forced
+    (``test_inputs``) and free-running, through the reference's own call stack in .eval().  Decoders get a small
+    max_decoder_steps so the free run stops on the step cap or on the done flags.  Stored: the state_dict, the
+    text / positions / speaker ids, the encoder output the decoder consumed, and the four returned values
+    (outputs, alignments, dones stacked, decoder_states) of both modes; plus the whole-model inference call."""
+    from deepvoice3_pytorch import builder
+    common = dict(n_vocab=149, mel_dim=80, padding_idx=0, dropout=0.0, max_positions=64)
+    cases = {
+        "inc_dv3": ("deepvoice3", dict(embed_dim=16, linear_dim=33, r=1, downsample_step=4, kernel_size=3,
+                                       encoder_channels=24, decoder_channels=16, converter_channels=16,
+                                       key_projection=True, value_projection=True,
+                                       force_monotonic_attention=True), 2),
+        "inc_dv3_k5_free": ("deepvoice3", dict(embed_dim=16, linear_dim=33, r=1, kernel_size=5,
+                                               encoder_channels=8, decoder_channels=16, converter_channels=16,
+                                               key_projection=False, value_projection=False,
+                                               force_monotonic_attention=False), 2),
+        # the reference's incremental speaker path broadcasts (B,1,C) + (B,C): only B = 1 is meaningful
+        "inc_dv3_ms": ("deepvoice3_multispeaker", dict(embed_dim=16, linear_dim=33, r=1, downsample_step=4,
+                                                       kernel_size=3, encoder_channels=24, decoder_channels=16,
+                                                       converter_channels=16, n_speakers=5, speaker_embed_dim=16,
+                                                       force_monotonic_attention=True), 1),
+        "inc_nyanko": ("nyanko", dict(embed_dim=12, linear_dim=33, r=1, downsample_step=4, kernel_size=3,
+                                      encoder_channels=16, decoder_channels=16, converter_channels=20,
+                                      force_monotonic_attention=True), 2),
+    }
+    fx = Fixture()
+    for ci, (name, (bname, kw, B)) in enumerate(cases.items()):
+        torch.manual_seed(5000 + ci)
+        kw = dict(common, **kw)
+        model = getattr(builder, bname)(**kw)
+        perturb(model, 177 + ci, scale=0.2)
+        model.eval()
+        dec = model.seq2seq.decoder
+        dec.max_decoder_steps, dec.min_decoder_steps = 14, 3
+        gen = torch.Generator().manual_seed(6000 + ci)
+        Ttext, Tdec = 9, 12
+        text = torch.randint(2, 149, (B, Ttext), generator=gen)
+        text_pos = torch.arange(1, Ttext + 1)[None, :].repeat(B, 1)
+        mel = torch.rand(B, Tdec, 80, generator=gen)
+        spk_ids = torch.tensor([3]) if kw.get("n_speakers", 1) > 1 else None
+        for k_, v_ in kw.items():
+            fx.put(name, "kw", k_, v_)
+        fx.put(name, "kw", "builder", bname)
+        for k_, v_ in model.state_dict().items():
+            fx.put(name, "sd", k_, v_)
+        fx.put(name, "in", "text", text)
+        fx.put(name, "in", "text_positions", text_pos)
+        fx.put(name, "in", "mel", mel)
+        if spk_ids is not None:
+            fx.put(name, "in", "speaker_ids", spk_ids)
+        fx.put(name, "meta", "max_decoder_steps", dec.max_decoder_steps)
+        fx.put(name, "meta", "min_decoder_steps", dec.min_decoder_steps)
+        with torch.no_grad():
+            spk = model.embed_speakers(spk_ids) if spk_ids is not None else None
+            if bname == "nyanko":
+                enc = model.seq2seq.encoder(text)
+            else:
+                enc = model.seq2seq.encoder(text, speaker_embed=spk)
+            fx.put(name, "in", "keys", enc[0])
+            fx.put(name, "in", "values", enc[1])
+            for mode in ("forced", "free"):
+                dec.start_fresh_sequence()
+                args = (enc, text_pos) if bname == "nyanko" else (enc, text_pos, spk)
+                outs = dec.incremental_forward(*args, test_inputs=mel if mode == "forced" else None)
+                outputs, alignments, dones, states = outs
+                fx.put(name, mode, "outputs", outputs)
+                fx.put(name, mode, "alignments", alignments)
+                fx.put(name, mode, "dones", torch.cat(dones, dim=1))      # (B, N, 1)
+                fx.put(name, mode, "states", states)
+            # the user-facing inference call (reference synthesis.py:62-64)
+            mel_o, lin_o, ali_o, done_o = model(text, text_positions=text_pos, speaker_ids=spk_ids)
+            fx.put(name, "model", "mel", mel_o)
+            fx.put(name, "model", "linear", lin_o)
+            fx.put(name, "model", "alignments", ali_o)
+            fx.put(name, "model", "dones", torch.cat(done_o, dim=1))
+        print(name, "forced", tuple(fx.d[name + "|forced|outputs"].shape), "free",
+              tuple(fx.d[name + "|free|outputs"].shape))
+    fx.save("incremental.npz")
+
+
 def conv_ramp_case():
     """reference tests/test_conv.py:10-63: causal conv, weights 1, bias 0, ramp input -> exact ints."""
     fx = Fixture()
@@ -293,9 +374,10 @@ if __name__ == "__main__":
     tmp = import_reference()
     try:
         torch.set_num_threads(1)  # deterministic reduction order
-        block_cases()
-        model_cases()
-        conv_ramp_case()
-        init_fingerprints()
+        only = set(sys.argv[1:])      # e.g. `make_golden.py incremental` regenerates that one fixture
+        for name, fn in (("blocks", block_cases), ("models", model_cases), ("conv_ramp", conv_ramp_case),
+                         ("init_fingerprints", init_fingerprints), ("incremental", incremental_cases)):
+            if not only or name in only:
+                fn()
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

@@ -144,6 +144,44 @@ def test_full_model(name):
     _check_case(case, outs, sd, ins)
 
 
+INCR = G.load("incremental.npz")
+
+
+def _incremental_oracle(case, mode):
+    """The oracle's stepwise decoder on one incremental fixture -> (outputs, alignments, dones (B,N,1), states)."""
+    from oracle import dv3_incremental as OI
+    kw = G.kwargs_of(case)
+    bname = kw.pop("builder")
+    fm = kw.pop("force_monotonic_attention")
+    spec = spec_from_builder(bname, **kw)
+    sd = G.tensors(case["sd"])
+    ins = G.tensors(case["in"])
+    common = dict(test_inputs=ins["mel"] if mode == "forced" else None, force_monotonic_attention=fm,
+                  min_decoder_steps=int(case["meta"]["min_decoder_steps"]),
+                  max_decoder_steps=int(case["meta"]["max_decoder_steps"]))
+    enc = (ins["keys"], ins["values"])
+    if bname == "nyanko":
+        outs = OI.nyanko_decoder_incremental(sd, spec, enc, ins["text_positions"], **common)
+    else:
+        spk = None
+        if "speaker_ids" in ins:
+            spk = torch.nn.functional.embedding(ins["speaker_ids"], sd["embed_speakers.weight"])
+        outs = OI.dv3_decoder_incremental(sd, spec, enc, ins["text_positions"], spk, **common)
+    return outs[0], outs[1], torch.cat(outs[2], dim=1), outs[3]
+
+
+@pytest.mark.parametrize("mode", ["forced", "free"])
+@pytest.mark.parametrize("name", list(INCR))
+def test_incremental_decoder(name, mode):
+    """Inference path of the oracle (oracle/dv3_incremental.py) against the live reference's
+    Decoder.incremental_forward, teacher-forced and free-running (same number of steps, same values)."""
+    case = INCR[name]
+    outs = _incremental_oracle(case, mode)
+    for got, key in zip(outs, ("outputs", "alignments", "dones", "states")):
+        assert tuple(got.shape) == tuple(case[mode][key].shape), key
+        close(got, case[mode][key])
+
+
 def test_audio_oracle_mel_basis_and_frames():
     """The one corroboration the reference tree offers for the (unpinned) audio path: its mel fixture of
     LJ001-0001 (212 893 samples) has 835 frames; and the Slaney filterbank equals torchaudio's."""
