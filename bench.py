@@ -202,7 +202,7 @@ def convblock_roofline(dev, pk, pk_kind):
         xs = torch.empty(2, Bc, T, C, device=dev, dtype=bf)
         ops.lib.call("dv3_tc_split_input", ops._p(x), ops._p(xs), 2, None, Bc, C, T, k, d, 0, 0.0, None, 0,
                      ops._stream())
-        name = "tcgen05 gated ConvBlock forward (persistent tc_conv_persist_kernel<GATED>) via dv3_tc_convblock_fwd"
+        name = "tcgen05 gated ConvBlock forward (persistent tap-reuse tc_conv_taps_kernel<GATED>) via dv3_tc_convblock_fwd"
 
         def launch():
             ops.lib.call("dv3_tc_convblock_fwd", ops._p(xs), ops._p(wfwd), 2, ops._p(bias), None, ops._p(x), ops._p(y),
@@ -240,9 +240,9 @@ def convblock_roofline(dev, pk, pk_kind):
              "issued_bf16_tflops": mma_passes * flops / t / 1e12,
              "issued_frac": mma_passes * flops / t / 1e12 / pk["bf16_tflops"],
              # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed
-             # `ncu --set full` capture (profiles/r01_ncu_full_tc_convblock_v2.csv): 59.9 MB + 32.0 MB per launch
+             # `ncu --set full` capture (profiles/r01_ncu_full_tc_convblock_v3.csv): 58.8 MB + 33.6 MB per launch
              # (it reads the bf16 hi/lo planes of the input and writes y + the two saved gate tensors)
-             "traffic": 91.95e6, "peak_source": pk_kind, "launch_us": t * 1e6, "alg_flops": flops, "math": math,
+             "traffic": 92.39e6, "peak_source": pk_kind, "launch_us": t * 1e6, "alg_flops": flops, "math": math,
              "hbm": hbm}
     else:
         r = dict(hbm, kernel="%s (B=16,C=512,T=800,k=3)" % name, traffic=None, peak_source=pk_kind,

@@ -148,9 +148,18 @@ class StepProgram:
 
     def run(self, n_steps, use_graph=True):
         if use_graph and self.graph is None:
+            # capture_begin/_end directly: the torch.cuda.graph() context manager also runs gc.collect() and
+            # empty_cache(), which cost more than the whole utterance (measured: 80-400 ms per call)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._launch_step()
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                self.graph.capture_begin()
+                try:
+                    self._launch_step()
+                finally:
+                    self.graph.capture_end()
+            torch.cuda.current_stream(self.dev).wait_stream(side)
         for _ in range(n_steps):
             if use_graph:
                 self.graph.replay()
