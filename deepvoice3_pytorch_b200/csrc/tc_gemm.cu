@@ -952,7 +952,9 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
     // 64-channel tiles (64 a | 64 b columns) when 128-channel tiles would leave most of the 148 SMs idle
     static int force_half = -1;
     if (force_half < 0) { const char* e = getenv("DV3_TC_FORCE_HALF"); force_half = (e && atoi(e) == 1) ? 1 : 0; }
-    const bool half = bk == 32 && cl == 1 && (force_half || (long long)t_tiles * (C / 128) * B < 100);
+    static int no_narrow = -1;          // DV3_TC_NO_NARROW=1: always 128-wide tiles (A/B experiments)
+    if (no_narrow < 0) { const char* e = getenv("DV3_TC_NO_NARROW"); no_narrow = (e && atoi(e) == 1) ? 1 : 0; }
+    const bool half = bk == 32 && cl == 1 && !no_narrow && (force_half || (long long)t_tiles * (C / 128) * B < 100);
     const int br = half ? 64 : 128;
     for (int pl = 0; pl < npl; ++pl) {
         if (encode_tmap_bf16_3d(&maps.a[pl], plane(xd, pl, (long long)B * T * C), C, T, B, (uint64_t)C * 2,
@@ -1013,7 +1015,9 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
     const int t_tiles = (T + 127) / 128;
     // tile width: two 128-column boxes only when that still fills the machine; 64 columns for small problems
     const bool wide = Nc > 128 && (long long)t_tiles * ((Nc + 255) / 256) * B >= 120;
-    const bool narrow = !wide && bk == 32 && cl == 1 && Nc > 64 && (k == 1 || Nc % 64 == 0) &&
+    static int no_narrow = -1;
+    if (no_narrow < 0) { const char* e = getenv("DV3_TC_NO_NARROW"); no_narrow = (e && atoi(e) == 1) ? 1 : 0; }
+    const bool narrow = !wide && !no_narrow && bk == 32 && cl == 1 && Nc > 64 && (k == 1 || Nc % 64 == 0) &&
                         (long long)t_tiles * ((Nc + 127) / 128) * B < 100;
     const int br = narrow ? 64 : 128;
     for (int pl = 0; pl < npl; ++pl) {
