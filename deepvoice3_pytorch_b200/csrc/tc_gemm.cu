@@ -51,6 +51,7 @@ struct TcParams {
     // wgrad
     float* dw; long long split_stride; int nsplit, batches_per_split;
     int msplit; long long s_m, s_mh, s_n, s_j;
+    int debug;                 // DV3_TC_DEBUG bit 0: epilogue skipped, bit 1: MMAs skipped (timing experiments only)
 };
 
 template <int BK> struct SwizzleOf;
@@ -519,6 +520,8 @@ static TapGeom tap_geom(int k, const int* tap_off) {
     g.stage = 2 * g.a_plane + 2 * k * NBOX * g.b_box;
     g.stages = (SMEM_LIMIT - 2048) / g.stage;
     if (g.stages > 6) g.stages = 6;
+    { static int cap = -1; if (cap < 0) { const char* e = getenv("DV3_TC_MAXSTAGES"); cap = e ? atoi(e) : 0; }
+      if (cap >= 2 && g.stages > cap) g.stages = cap; }
     // debugging aid: DV3_TC_TAPS_BASEOFF=1 also writes (start >> 7) & 7 into the descriptor's base-offset field
     static int bo = -1;
     if (bo < 0) { const char* e = getenv("DV3_TC_TAPS_BASEOFF"); bo = (e && atoi(e) == 1) ? 1 : 0; }
@@ -614,6 +617,7 @@ tc_conv_taps_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
                         const uint64_t adv = (uint64_t)(kk * 2);
+                        if (p.debug & 2) continue;
                         umma_bf16(acc, da0 + adv, db0 + adv, idesc2, (kb | j | kk) != 0);   // p0 x [p0 ; p1]
                         umma_bf16(acc + NCOLS, da1 + adv, db0 + adv, idesc, 1);
                     }
@@ -632,8 +636,10 @@ tc_conv_taps_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
             mbar_wait(&tfull[a], aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + a * 2 * NCOLS + ((uint32_t)(q * 32) << 16);
-            if (MODE == TC_GATED) epilogue_gated<BR, NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
-            else epilogue_conv<NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+            if (!(p.debug & 1)) {
+                if (MODE == TC_GATED) epilogue_gated<BR, NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+                else epilogue_conv<NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+            }
             tc_fence_before();
             mbar_arrive(&tempty[a]);
         }
@@ -659,6 +665,193 @@ static int launch_tc_taps(const TcMaps& maps, const TcParams& p, const TapGeom& 
     const int grid = num_tiles < sms ? num_tiles : sms;
     const int smem = g.stages * g.stage + 1024 + 512;
     kern<<<grid, TC_THREADS, smem, st>>>(maps, p, g, tiles_x, tiles_y, num_tiles);
+    return check_launch(what);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant of the tap-reuse kernel (tcgen05 cta_group::2).  The shared-memory port is what bounds the
+// kernels above (operand reads by the MMAs + TMA writes <= 128 B/clk/SM); in a pair the two SMs of a TPC execute one
+// M = 256 MMA: each reads its OWN 128 activation rows (CTA r = batch 2*bp + r, same time tile, same output
+// channels) but only HALF of the weight rows, so weight bytes fetched, written and read per SM halve.
+// With the split-bf16 scheme the halves fall out naturally:
+//     MMA 1:  p0(A) x [p0(W) ; p1(W)]   N = 256   -> CTA 0 holds p0(W) (128 rows), CTA 1 holds p1(W)
+//     MMA 2:  p1(A) x  p0(W)            N = 128   -> CTA 0 holds rows 0..63 of p0(W), CTA 1 rows 64..127
+// Per CTA and tap: 12 KB of weights instead of 16 KB, 14 KB of operand reads per K=16 step instead of 20 KB.
+// Protocol: both CTAs run a TMA producer; all loads of a stage credit the LEADER's full barrier; the leader's MMA
+// thread issues for the pair and its commits arrive on the empty / accumulator-full barriers of BOTH CTAs; the
+// epilogue warps of both CTAs release an accumulator set by arriving on the leader's barrier (256 arrivals).
+// ------------------------------------------------------------------------------------------------
+struct PairGeom { int a_rows, a_plane, stage, stages, off_min; };
+
+static PairGeom pair_geom(int k, const int* tap_off) {
+    int lo = tap_off[0], hi = tap_off[0];
+    for (int j = 1; j < k; ++j) { lo = tap_off[j] < lo ? tap_off[j] : lo; hi = tap_off[j] > hi ? tap_off[j] : hi; }
+    PairGeom g;
+    g.off_min = lo;
+    g.a_rows = (128 + (hi - lo) + 7) / 8 * 8;
+    g.a_plane = (g.a_rows * 64 + 1023) / 1024 * 1024;
+    g.stage = 2 * g.a_plane + k * 12288;
+    g.stages = (SMEM_LIMIT - 2048) / g.stage;
+    if (g.stages > 6) g.stages = 6;
+    { static int cap = -1; if (cap < 0) { const char* e = getenv("DV3_TC_MAXSTAGES"); cap = e ? atoi(e) : 0; }
+      if (cap >= 2 && g.stages > cap) g.stages = cap; }
+    return g;
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_conv_pair_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p,
+                    const __grid_constant__ PairGeom g, int tiles_x, int tiles_y, int num_tiles) {
+    constexpr int BK = 32, NCOLS = 128;
+    constexpr int B_TAP = 12288;                        // per tap: [plane r: 128 rows][p0 rows 64r..64r+63]
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int STAGES = g.stages, STAGE = g.stage;
+    const int B_OFF = 2 * g.a_plane;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_iters = p.kb_n;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.a[1]); prefetch_tmap(&maps.b[0]); prefetch_tmap(&maps.b[1]);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    cluster_sync_all();                                 // both CTAs' barriers exist before any remote signal
+    if (warp == 1) tmem_alloc_pair<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // pair tile -> (time tile, channel tile, batch pair); this CTA's batch = 2*pair + rank
+    auto decode = [&](int tile, int& a_row0, int& a_z, int& b_row0, int& b_row1) {
+        const int ty = tile % tiles_y, r = tile / tiles_y;
+        const int tx = r % tiles_x;
+        a_z = 2 * (r / tiles_x) + (int)rank;
+        a_row0 = tx * 128;
+        if (MODE == TC_GATED) { b_row0 = ty * 64; b_row1 = p.Nc + ty * 64; }
+        else { b_row0 = ty * 128; b_row1 = b_row0 + 64; }
+    };
+
+    if (warp == 0 && lane == 0) {
+        int it = 0;
+        const uint32_t stage_tx = 2u * (uint32_t)(2 * g.a_rows * 64 + p.k * B_TAP);     // both CTAs' bytes
+        for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+            int a_row0, a_z, b_row0, b_row1;
+            decode(tile, a_row0, a_z, b_row0, b_row1);
+            for (int kb = 0; kb < n_iters; ++kb, ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait_cluster(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * STAGE;
+                const int ax = kb * BK;
+                if (rank == 0) mbar_arrive_expect_tx(&full[s], stage_tx);
+                const uint32_t lead_full = mapa_u32(&full[s], 0);
+                tma_load_3d_pair(st, &maps.a[0], lead_full, ax, a_row0 + g.off_min, a_z);
+                tma_load_3d_pair(st + g.a_plane, &maps.a[1], lead_full, ax, a_row0 + g.off_min, a_z);
+                for (int j = 0; j < p.k; ++j) {
+                    uint8_t* bd = st + B_OFF + j * B_TAP;
+                    const int r0 = j * p.rows_per_tap + b_row0, r1 = j * p.rows_per_tap + b_row1;
+                    // this CTA's half of [p0 ; p1]: plane `rank`, both 64-row boxes
+                    tma_load_3d_pair(bd, &maps.b[rank], lead_full, ax, r0, 0);
+                    tma_load_3d_pair(bd + 4096, &maps.b[rank], lead_full, ax, r1, 0);
+                    // this CTA's half of p0: box `rank`
+                    tma_load_3d_pair(bd + 8192, &maps.b[0], lead_full, ax, rank == 0 ? r0 : r1, 0);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        constexpr uint32_t idesc1 = make_idesc_bf16(256, 2 * NCOLS), idesc2 = make_idesc_bf16(256, NCOLS);
+        int it = 0, tcount = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++tcount) {
+            const int a = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait_cluster(&tempty[a], aph ^ 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + a * 2 * NCOLS;
+            for (int kb = 0; kb < n_iters; ++kb, ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait_cluster(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE);
+                for (int j = 0; j < p.k; ++j) {
+                    const uint32_t ashift = (uint32_t)(p.tap_off[j] - g.off_min) * 64u;
+                    const uint64_t da0 = make_desc<BK>(sa + ashift), da1 = make_desc<BK>(sa + g.a_plane + ashift);
+                    const uint64_t dby = make_desc<BK>(sa + B_OFF + j * B_TAP);
+                    const uint64_t dbx = make_desc<BK>(sa + B_OFF + j * B_TAP + 8192);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        if (p.debug & 2) continue;
+                        umma_bf16_pair(acc, da0 + adv, dby + adv, idesc1, (kb | j | kk) != 0);   // p0 x [p0 ; p1]
+                        umma_bf16_pair(acc + NCOLS, da1 + adv, dbx + adv, idesc2, 1);            // p1 x p0
+                    }
+                }
+                umma_commit_pair(&empty[s]);
+            }
+            umma_commit_pair(&tfull[a]);
+        }
+    } else if (warp >= 2) {
+        const int q = warp & 3, row = q * 32 + lane;
+        int tcount = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++tcount) {
+            int a_row0, a_z, b_row0, b_row1;
+            decode(tile, a_row0, a_z, b_row0, b_row1);
+            const int a = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait_cluster(&tfull[a], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + a * 2 * NCOLS + ((uint32_t)(q * 32) << 16);
+            if (!(p.debug & 1)) {
+                if (MODE == TC_GATED) epilogue_gated<64, NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+                else epilogue_conv<NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+            }
+            tc_fence_before();
+            if (rank == 0) mbar_arrive(&tempty[a]);
+            else mbar_arrive_remote(&tempty[a], 0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                 // the peer's shared memory / barriers stay alive until both are done
+    if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
+}
+
+static int g_pair = -1;
+static int tc_pair() {                     // DV3_TC_PAIR: 0 = off, 1 = when there are more tiles than SMs, 2 = whenever possible
+    if (g_pair < 0) { const char* e = getenv("DV3_TC_PAIR"); g_pair = e ? atoi(e) : 0; }
+    return g_pair;
+}
+static bool pair_usable(int B, int k, const int* tap_off, long long num_tiles64) {
+    const int mode = tc_pair();
+    if (mode <= 0 || (B & 1) || (mode == 1 && num_tiles64 <= 148)) return false;
+    const PairGeom g = pair_geom(k, tap_off);
+    return g.a_rows <= 256 && g.stages >= 2;
+}
+
+template <int MODE>
+static int launch_tc_pair(const TcMaps& maps, const TcParams& p, const PairGeom& g, int tiles_x, int tiles_y,
+                          int batch, cudaStream_t st, const char* what) {
+    static bool configured = false;
+    auto kern = tc_conv_pair_kernel<MODE>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) { set_error("%s: cannot set %d B dynamic smem: %s", what, SMEM_LIMIT, cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int num_tiles = tiles_x * tiles_y * (batch / 2);
+    int clusters = sms / 2;
+    if (num_tiles < clusters) clusters = num_tiles;
+    const int smem = g.stages * g.stage + 1024 + 512;
+    kern<<<2 * clusters, TC_THREADS, smem, st>>>(maps, p, g, tiles_x, tiles_y, num_tiles);
     return check_launch(what);
 }
 
@@ -695,6 +888,7 @@ struct TcMnParams {
     uint32_t lbo, sbo;                        // descriptor strides in bytes (chunk stride, 8-row group stride)
     float* dw; long long split_stride;
     int msplit; long long s_m, s_mh, s_n, s_j;
+    int debug;                 // DV3_TC_DEBUG bit 0: epilogue skipped, bit 1: MMAs skipped (timing experiments only)
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -970,8 +1164,20 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
     fill_taps_tc(p.tap_off, k, dilation, causal, false);
     p.bias = bias; p.spk = spk; p.res = res; p.y = y; p.save_a = save_a; p.save_s = save_s;
     p.gate_mode = mode; p.residual = residual;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DV3_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     dim3 grid(t_tiles, C / br, B);
     cudaStream_t st = (cudaStream_t)stream;
+    // CTA pairs (cta_group::2): two batches per M = 256 MMA, weights fetched once per pair
+    if (bk == 32 && cl == 1 && pair_usable(B, k, p.tap_off, (long long)t_tiles * (C / 64) * B)) {
+        const PairGeom g = pair_geom(k, p.tap_off);
+        for (int pl = 0; pl < 2; ++pl) {
+            if (encode_tmap_bf16_3d(&maps.a[pl], plane(xd, pl, (long long)B * T * C), C, T, B, (uint64_t)C * 2,
+                                    (uint64_t)T * C * 2, bk, g.a_rows)) return 1;
+            if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
+                                    (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 64)) return 1;
+        }
+        return launch_tc_pair<TC_GATED>(maps, p, g, t_tiles, C / 64, B, st, "tc_convblock_fwd(pair)");
+    }
     // k > 1: the tap-reuse kernel (activation rows fetched once per 32-channel slice instead of once per tap)
     if (bk == 32 && cl == 1 && taps_usable<2, 64>(k, p.tap_off, (long long)t_tiles * (C / 64) * B)) {
         const TapGeom g = tap_geom<2, 64>(k, p.tap_off);
@@ -1033,7 +1239,18 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
     fill_taps_tc(p.tap_off, k, dilation, causal, transpose_taps != 0);
     p.out = out; p.bias = bias; p.relu = relu; p.e1 = e1; p.e2 = e2; p.alpha = alpha; p.addmode = addmode;
     p.p_drop = p_drop; p.seed_ptr = seed_ptr; p.salt = salt;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DV3_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (bk == 32 && cl == 1 && Nc % 128 == 0 && pair_usable(B, k, p.tap_off, (long long)t_tiles * (Nc / 128) * B)) {
+        const PairGeom g = pair_geom(k, p.tap_off);
+        for (int pl = 0; pl < 2; ++pl) {
+            if (encode_tmap_bf16_3d(&maps.a[pl], plane(a, pl, (long long)B * T * Kp), Kc, T, B, (uint64_t)Kp * 2,
+                                    (uint64_t)T * Kp * 2, bk, g.a_rows)) return 1;
+            if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
+                                    (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, 64)) return 1;
+        }
+        return launch_tc_pair<TC_CONV>(maps, p, g, t_tiles, Nc / 128, B, st, "tc_conv(pair)");
+    }
     if (bk == 32 && cl == 1 && k > 1) {
         // k-tap conv / data gradient: tap-reuse kernel, 64-column tiles when 128-column ones cannot fill the machine
         const bool n64 = narrow && !((long long)t_tiles * ((Nc + 127) / 128) * B > 148);

@@ -10,7 +10,10 @@ from deepvoice3_pytorch_b200 import ops  # noqa: E402
 
 ops.conv_math = "tc"
 dev = "cuda"
-for (B, C, T, k, d) in [(16, 512, 800, 3, 1), (16, 512, 800, 3, 27), (16, 256, 800, 3, 3), (16, 512, 128, 3, 9), (16, 256, 200, 3, 9)]:
+SHAPES = [(16, 512, 800, 3, 1), (16, 512, 800, 3, 27), (16, 256, 800, 3, 3), (16, 512, 128, 3, 9), (16, 256, 200, 3, 9)]
+if os.environ.get("TC_TIME_FIRST"):
+    SHAPES = SHAPES[:int(os.environ["TC_TIME_FIRST"])]
+for (B, C, T, k, d) in SHAPES:
     v = (torch.randn(2 * C, C, k, device=dev) * (4.0 / (k * C)) ** 0.5).requires_grad_(True)
     g = v.detach().pow(2).sum((1, 2), keepdim=True).sqrt().requires_grad_(True)
     bias = torch.zeros(2 * C, device=dev, requires_grad=True)
@@ -25,6 +28,8 @@ for (B, C, T, k, d) in [(16, 512, 800, 3, 1), (16, 512, 800, 3, 27), (16, 256, 8
     for e in prof.key_averages():
         if "tc_conv_kernel" in e.key:
             rows[e.key.split("tc_conv_kernel")[1][:18]] = e.device_time_total / e.count
+        elif "tc_conv_pair" in e.key:
+            rows["pair" + e.key.split("tc_conv_pair_kernel")[1][:4]] = e.device_time_total / e.count
         elif "tc_conv_taps" in e.key:
             rows["taps" + e.key.split("tc_conv_taps_kernel")[1][:10]] = e.device_time_total / e.count
         elif "tc_conv_persist" in e.key:
