@@ -529,7 +529,11 @@ static TapGeom tap_geom(int k, const int* tap_off) {
     return g;
 }
 
-template <int MODE, int NBOX, int BR>
+// CL = 2: the two CTAs of a cluster work on two BATCHES of the same (time tile, channel tile): they need the same
+// weight boxes, so CTA r fetches only weight plane r of every tap and TMA-multicasts it into both shared memories
+// (the kernel is L2-feed bound and weights are 3/4 of its bytes: 64.6 -> 40.6 KB per CTA and channel slice).
+// empty[s] then collects one commit from each CTA (the peer's producer writes into this CTA's stage too).
+template <int MODE, int NBOX, int BR, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_taps_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p,
                     const __grid_constant__ TapGeom g, int tiles_x, int tiles_y, int num_tiles) {
@@ -548,23 +552,27 @@ tc_conv_taps_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_iters = p.kb_n;                         // one stage per 32-channel slice, all taps inside
+    const uint32_t rank = CL > 1 ? cluster_ctarank() : 0;
+    const int first_tile = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+    const int tile_step = CL > 1 ? (int)(gridDim.x / CL) : (int)gridDim.x;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.a[1]); prefetch_tmap(&maps.b[0]); prefetch_tmap(&maps.b[1]);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<4 * NCOLS>(tmem_ptr);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                    // the peer's barriers exist before anything is multicast into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
     auto decode = [&](int tile, int& a_row0, int& a_z, int& b_row0, int& b_row1) {
         const int ty = tile % tiles_y, r = tile / tiles_y;
         const int tx = r % tiles_x;
-        a_z = r / tiles_x;
+        a_z = CL * (r / tiles_x) + (int)rank;
         a_row0 = tx * 128;
         if (MODE == TC_GATED) { b_row0 = ty * BR; b_row1 = p.Nc + ty * BR; }
         else { b_row0 = ty * BR * NBOX; b_row1 = b_row0 + BR; }
@@ -572,7 +580,7 @@ tc_conv_taps_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
 
     if (warp == 0 && lane == 0) {
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
             int a_row0, a_z, b_row0, b_row1;
             decode(tile, a_row0, a_z, b_row0, b_row1);
             for (int kb = 0; kb < n_iters; ++kb, ++it) {
@@ -584,11 +592,19 @@ tc_conv_taps_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
 #pragma unroll
                 for (int pl = 0; pl < NPL; ++pl) {
                     tma_load_3d(st + pl * g.a_plane, &maps.a[pl], &full[s], ax, a_row0 + g.off_min, a_z);
+                    if (CL > 1 && pl != (int)rank) continue;       // the peer multicasts the other weight plane
                     for (int j = 0; j < p.k; ++j) {
                         uint8_t* bdst = st + B_OFF + (j * NPL + pl) * NBOX * g.b_box;
-                        tma_load_3d(bdst, &maps.b[pl], &full[s], ax, j * p.rows_per_tap + b_row0, 0);
-                        if (NBOX == 2)
-                            tma_load_3d(bdst + g.b_box, &maps.b[pl], &full[s], ax, j * p.rows_per_tap + b_row1, 0);
+                        if (CL > 1) {
+                            tma_load_3d_multicast(bdst, &maps.b[pl], &full[s], ax, j * p.rows_per_tap + b_row0, 0, 3);
+                            if (NBOX == 2)
+                                tma_load_3d_multicast(bdst + g.b_box, &maps.b[pl], &full[s], ax,
+                                                      j * p.rows_per_tap + b_row1, 0, 3);
+                        } else {
+                            tma_load_3d(bdst, &maps.b[pl], &full[s], ax, j * p.rows_per_tap + b_row0, 0);
+                            if (NBOX == 2)
+                                tma_load_3d(bdst + g.b_box, &maps.b[pl], &full[s], ax, j * p.rows_per_tap + b_row1, 0);
+                        }
                     }
                 }
             }
@@ -596,7 +612,7 @@ tc_conv_taps_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
     } else if (warp == 1 && lane == 0) {
         constexpr uint32_t idesc = make_idesc_bf16(128, NCOLS), idesc2 = make_idesc_bf16(128, 2 * NCOLS);
         int it = 0, tcount = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++tcount) {
             const int a = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait(&tempty[a], aph ^ 1);
             tc_fence_after();
@@ -622,14 +638,15 @@ tc_conv_taps_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
                         umma_bf16(acc + NCOLS, da1 + adv, db0 + adv, idesc, 1);
                     }
                 }
-                umma_commit(&empty[s]);
+                if (CL > 1) umma_commit_multicast(&empty[s], 3);     // the stage is free once BOTH CTAs consumed it
+                else umma_commit(&empty[s]);
             }
             umma_commit(&tfull[a]);
         }
     } else if (warp >= 2) {
         const int q = warp & 3, row = q * 32 + lane;
         int tcount = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++tcount) {
             int a_row0, a_z, b_row0, b_row1;
             decode(tile, a_row0, a_z, b_row0, b_row1);
             const int a = tcount & 1, aph = (tcount >> 1) & 1;
@@ -646,14 +663,15 @@ tc_conv_taps_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                    // no CTA exits while its peer still multicasts into / signals it
     if (warp == 1) tmem_dealloc<4 * NCOLS>(tmem_base);
 }
 
-template <int MODE, int NBOX, int BR>
+template <int MODE, int NBOX, int BR, int CL = 1>
 static int launch_tc_taps(const TcMaps& maps, const TcParams& p, const TapGeom& g, int tiles_x, int tiles_y, int batch,
                           cudaStream_t st, const char* what) {
     static bool configured = false;
-    auto kern = tc_conv_taps_kernel<MODE, NBOX, BR>;
+    auto kern = tc_conv_taps_kernel<MODE, NBOX, BR, CL>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) { set_error("%s: cannot set %d B dynamic smem: %s", what, SMEM_LIMIT, cudaGetErrorString(e)); return 1; }
@@ -661,10 +679,24 @@ static int launch_tc_taps(const TcMaps& maps, const TcParams& p, const TapGeom& 
     }
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-    const int num_tiles = tiles_x * tiles_y * batch;
-    const int grid = num_tiles < sms ? num_tiles : sms;
     const int smem = g.stages * g.stage + 1024 + 512;
-    kern<<<grid, TC_THREADS, smem, st>>>(maps, p, g, tiles_x, tiles_y, num_tiles);
+    if (CL == 1) {
+        const int num_tiles = tiles_x * tiles_y * batch;
+        const int grid = num_tiles < sms ? num_tiles : sms;
+        kern<<<grid, TC_THREADS, smem, st>>>(maps, p, g, tiles_x, tiles_y, num_tiles);
+    } else {
+        const int num_tiles = tiles_x * tiles_y * (batch / CL);      // cluster work units
+        int clusters = sms / CL;
+        if (num_tiles < clusters) clusters = num_tiles;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, p, g, tiles_x, tiles_y, num_tiles);
+        if (e != cudaSuccess) { set_error("%s: cluster launch failed: %s", what, cudaGetErrorString(e)); return 1; }
+    }
     return check_launch(what);
 }
 
@@ -864,6 +896,12 @@ static int tc_taps() {                     // DV3_TC_TAPS: 0 = off, 1 = when the
 // usable when every tap fits one TMA box (<= 256 rows) and at least two stages fit in shared memory.  Measured
 // (tools/tc_time.py): 7-10 % faster than the per-tap persistent kernel on the (16,512,800) blocks, on par at
 // (16,256,800), 2-4 % slower on the <= 148-tile shapes (coarser stages, longer pipeline fill) -> default = mode 1.
+static int g_mcast = -1;
+static bool taps_mcast(int B) {            // DV3_TC_MCAST=1: weight multicast across 2-CTA clusters (even batch sizes)
+    if (g_mcast < 0) { const char* e = getenv("DV3_TC_MCAST"); g_mcast = e ? atoi(e) : 0; }
+    return g_mcast > 0 && (B & 1) == 0;
+}
+
 template <int NBOX, int BR>
 static bool taps_usable(int k, const int* tap_off, long long num_tiles) {
     const int mode = tc_taps();
@@ -1187,6 +1225,7 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
             if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
                                     (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 64)) return 1;
         }
+        if (taps_mcast(B)) return launch_tc_taps<TC_GATED, 2, 64, 2>(maps, p, g, t_tiles, C / 64, B, st, "tc_convblock_fwd(taps,mcast)");
         return launch_tc_taps<TC_GATED, 2, 64>(maps, p, g, t_tiles, C / 64, B, st, "tc_convblock_fwd(taps)");
     }
     // more tiles than SMs: the persistent kernel (64 a | 64 b columns per tile, double-buffered accumulators)
@@ -1265,6 +1304,7 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
                                         (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, n64 ? 64 : 128)) return 1;
             }
             if (n64) return launch_tc_taps<TC_CONV, 1, 64>(maps, p, g, t_tiles, Nc / 64, B, st, "tc_conv(taps64)");
+            if (taps_mcast(B)) return launch_tc_taps<TC_CONV, 1, 128, 2>(maps, p, g, t_tiles, Nc / 128, B, st, "tc_conv(taps,mcast)");
             return launch_tc_taps<TC_CONV, 1, 128>(maps, p, g, t_tiles, Nc / 128, B, st, "tc_conv(taps)");
         }
     }
