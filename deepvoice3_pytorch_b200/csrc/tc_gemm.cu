@@ -51,7 +51,7 @@ struct TcParams {
     // wgrad
     float* dw; long long split_stride; int nsplit, batches_per_split;
     int msplit; long long s_m, s_mh, s_n, s_j;
-    int debug;                 // DV3_TC_DEBUG bit 0: epilogue skipped, bit 1: MMAs skipped (timing experiments only)
+    int debug;                 // DV3_TC_DEBUG bit 0: epilogue skipped, bit 1: MMAs skipped, bit 2: TMA loads skipped (timing experiments only)
 };
 
 template <int BK> struct SwizzleOf;
@@ -358,11 +358,11 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 // boundaries; barrier / TMEM / tensor-map set-up is paid once per SM instead of once per tile.
 // N per tile is limited to 128 columns (4 x 128 = 512 TMEM columns).
 // ------------------------------------------------------------------------------------------------
-template <int MODE, int NBOX, int BR>
+template <int MODE, int NBOX, int BR, int BK = 32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_persist_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p, int tiles_x,
                        int tiles_y, int num_tiles) {
-    constexpr int BK = 32, NPL = 2;
+    constexpr int NPL = 2;
     using Cfg = TcCfg<NBOX, BK, NPL, BR>;
     constexpr int TILE = Cfg::TILE, TILE_B = Cfg::TILE_B, STAGE = Cfg::STAGE, STAGES = Cfg::STAGES, NCOLS = Cfg::NCOLS;
     constexpr int B_OFF = NPL * TILE;
@@ -412,6 +412,7 @@ tc_conv_persist_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
                 const int j = kit / p.kb_n, kb = kit - j * p.kb_n;
                 const int ax = kb * BK, ay = a_row0 + p.tap_off[j];
                 const int by0 = j * p.rows_per_tap + b_row0, by1 = j * p.rows_per_tap + b_row1;
+                if (p.debug & 4) { mbar_arrive(&full[s]); continue; }
                 mbar_arrive_expect_tx(&full[s], STAGE);
 #pragma unroll
                 for (int pl = 0; pl < NPL; ++pl) {
@@ -440,6 +441,7 @@ tc_conv_persist_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
 #pragma unroll
                 for (int kk = 0; kk < BK / 16; ++kk) {
                     const uint64_t adv = (uint64_t)(kk * 2);
+                    if (p.debug & 2) continue;
                     umma_bf16(acc, da0 + adv, db0 + adv, idesc2, (kit | kk) != 0);     // p0 x [p0 ; p1] -> main | cross
                     umma_bf16(acc + NCOLS, da1 + adv, db0 + adv, idesc, 1);
                 }
@@ -457,8 +459,10 @@ tc_conv_persist_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
             mbar_wait(&tfull[a], aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + a * 2 * NCOLS + ((uint32_t)(q * 32) << 16);
-            if (MODE == TC_GATED) epilogue_gated<BR, NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
-            else epilogue_conv<NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+            if (!(p.debug & 1)) {
+                if (MODE == TC_GATED) epilogue_gated<BR, NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+                else epilogue_conv<NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+            }
             tc_fence_before();
             mbar_arrive(&tempty[a]);                                // 128 arrivals release the set to the MMA thread
         }
@@ -468,13 +472,13 @@ tc_conv_persist_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
     if (warp == 1) tmem_dealloc<4 * NCOLS>(tmem_base);
 }
 
-template <int MODE, int NBOX, int BR>
+template <int MODE, int NBOX, int BR, int BK = 32>
 static int launch_tc_persist(const TcMaps& maps, const TcParams& p, int tiles_x, int tiles_y, int batch,
                              cudaStream_t st, const char* what) {
-    using Cfg = TcCfg<NBOX, 32, 2, BR>;
+    using Cfg = TcCfg<NBOX, BK, 2, BR>;
     constexpr int SMEM = Cfg::STAGES * Cfg::STAGE + 1024 + 512;
     static bool configured = false;
-    auto kern = tc_conv_persist_kernel<MODE, NBOX, BR>;
+    auto kern = tc_conv_persist_kernel<MODE, NBOX, BR, BK>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) { set_error("%s: cannot set %d B dynamic smem: %s", what, SMEM, cudaGetErrorString(e)); return 1; }
@@ -588,6 +592,7 @@ tc_conv_taps_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
                 mbar_wait(&empty[s], ph ^ 1);
                 uint8_t* st = smem + s * STAGE;
                 const int ax = kb * BK;
+                if (CL == 1 && (p.debug & 4)) { mbar_arrive(&full[s]); continue; }   // timing experiment: no loads at all
                 mbar_arrive_expect_tx(&full[s], NPL * (g.a_rows * 64 + B_PLANE));
 #pragma unroll
                 for (int pl = 0; pl < NPL; ++pl) {
@@ -887,15 +892,28 @@ static int launch_tc_pair(const TcMaps& maps, const TcParams& p, const PairGeom&
     return check_launch(what);
 }
 
+static int persist_bk() {                 // 128-byte rows / SWIZZLE_128B in the persistent kernels; DV3_TC_PERSIST_BK=32: 64-byte rows
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DV3_TC_PERSIST_BK"); v = (e && atoi(e) == 32) ? 32 : 64; }
+    return v;
+}
+static int small_bk() {                   // DV3_TC_SMALL_BK=32: the same for the one-tile-per-CTA kernels
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DV3_TC_SMALL_BK"); v = (e && atoi(e) == 32) ? 32 : 64; }
+    return v;
+}
+
 static int g_taps = -1;
-static int tc_taps() {                     // DV3_TC_TAPS: 0 = off, 1 = when there are more tiles than SMs, 2 = always
-    if (g_taps < 0) { const char* e = getenv("DV3_TC_TAPS"); g_taps = e ? atoi(e) : 1; }
+static int tc_taps() {                     // DV3_TC_TAPS: 0 = off (default), 1 = when there are more tiles than SMs, 2 = always
+    if (g_taps < 0) { const char* e = getenv("DV3_TC_TAPS"); g_taps = e ? atoi(e) : 0; }
     return g_taps;
 }
 
 // usable when every tap fits one TMA box (<= 256 rows) and at least two stages fit in shared memory.  Measured
 // (tools/tc_time.py): 7-10 % faster than the per-tap persistent kernel on the (16,512,800) blocks, on par at
-// (16,256,800), 2-4 % slower on the <= 148-tile shapes (coarser stages, longer pipeline fill) -> default = mode 1.
+// (16,256,800), 2-4 % slower on the <= 148-tile shapes (coarser stages, longer pipeline fill); but its row-shifted
+// descriptors make the MMAs themselves ~18 % slower (MMA-only time 105 vs 89 us) and the BK = 64 persistent kernel beats
+// it (107 vs 119 us) -> opt-in only.
 static int g_mcast = -1;
 static bool taps_mcast(int B) {            // DV3_TC_MCAST=1: weight multicast across 2-CTA clusters (even batch sizes)
     if (g_mcast < 0) { const char* e = getenv("DV3_TC_MCAST"); g_mcast = e ? atoi(e) : 0; }
@@ -926,7 +944,7 @@ struct TcMnParams {
     uint32_t lbo, sbo;                        // descriptor strides in bytes (chunk stride, 8-row group stride)
     float* dw; long long split_stride;
     int msplit; long long s_m, s_mh, s_n, s_j;
-    int debug;                 // DV3_TC_DEBUG bit 0: epilogue skipped, bit 1: MMAs skipped (timing experiments only)
+    int debug;                 // DV3_TC_DEBUG bit 0: epilogue skipped, bit 1: MMAs skipped, bit 2: TMA loads skipped (timing experiments only)
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -1171,81 +1189,97 @@ int dv3_tc_conv_supported(int B, int Cin, int Cout, int T, int k) {
 }
 
 // Gated forward.  xd: [npl][B][T][C] bf16 planes of the (dropped-out) input; w: [npl][k][2C][C] bf16 planes of the
-// normalised weight; npl = 2 ("x3") or 3 ("x6"); the rest as dv3_convblock_fwd.
+// normalised weight; npl = 2; the rest as dv3_convblock_fwd.
+//
+// Kernel selection (measured, tools/tc_time.py / bench.py on the B200):
+//   more 64-channel tiles than SMs  -> persistent kernel, 128-byte operand rows (BK = 64, SWIZZLE_128B)
+//   128-wide tiles would leave SMs idle -> one 64-channel tile per CTA, BK = 64
+//   otherwise                        -> one 128-channel tile per CTA (N = 256), BK = 32
+// BK = 64 halves the number of TMA operations and mbarrier round trips per byte and makes every L2 request a full
+// 128-byte line: 10-25 % faster than BK = 32 on every shape once the epilogue stopped being the bottleneck.
+// Opt-in experiments (all parity-clean, none faster): DV3_TC_TAPS (tap reuse), DV3_TC_MCAST (weight multicast),
+// DV3_TC_PAIR (cta_group::2), DV3_TC_CLUSTER (multicast in the one-tile kernels).
 int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bias, const float* spk,
                          const float* res, float* y, float* save_a, float* save_s, int B, int C, int T, int k,
                          int dilation, int causal, int mode, int residual, void* stream) {
     DV3_REQUIRE(dv3_tc_supported(B, C, T, k), "tc_convblock_fwd: unsupported shape B=%d C=%d T=%d k=%d", B, C, T, k);
     DV3_REQUIRE(npl == 2, "tc_convblock_fwd: npl must be 2");
-    const int bk = tc_bk();
     TcMaps maps;
     const int cl = pick_cluster(B);
     const int t_tiles = (T + 127) / 128;
-    // 64-channel tiles (64 a | 64 b columns) when 128-channel tiles would leave most of the 148 SMs idle
-    static int force_half = -1;
-    if (force_half < 0) { const char* e = getenv("DV3_TC_FORCE_HALF"); force_half = (e && atoi(e) == 1) ? 1 : 0; }
-    static int no_narrow = -1;          // DV3_TC_NO_NARROW=1: always 128-wide tiles (A/B experiments)
-    if (no_narrow < 0) { const char* e = getenv("DV3_TC_NO_NARROW"); no_narrow = (e && atoi(e) == 1) ? 1 : 0; }
-    const bool half = bk == 32 && cl == 1 && !no_narrow && (force_half || (long long)t_tiles * (C / 128) * B < 100);
-    const int br = half ? 64 : 128;
-    for (int pl = 0; pl < npl; ++pl) {
-        if (encode_tmap_bf16_3d(&maps.a[pl], plane(xd, pl, (long long)B * T * C), C, T, B, (uint64_t)C * 2,
-                                (uint64_t)T * C * 2, bk, 128)) return 1;
-        if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
-                                (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, br)) return 1;
-        if (cl > 1 && encode_tmap_bf16_3d(&maps.bs[pl], plane(w, pl, (long long)k * 2 * C * C), C,
-                                          (uint64_t)k * 2 * C, 1, (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk,
-                                          128 / cl)) return 1;
-    }
+    cudaStream_t st = (cudaStream_t)stream;
+    // tensor maps for a given K-block width and box heights (activation rows, weight rows)
+    auto enc = [&](int bkx, int a_rows, int b_rows) -> int {
+        for (int pl = 0; pl < 2; ++pl) {
+            if (encode_tmap_bf16_3d(&maps.a[pl], plane(xd, pl, (long long)B * T * C), C, T, B, (uint64_t)C * 2,
+                                    (uint64_t)T * C * 2, bkx, a_rows)) return 1;
+            if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
+                                    (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bkx, b_rows)) return 1;
+        }
+        return 0;
+    };
     TcParams p = {};
-    p.T = T; p.B = B; p.Kc = C; p.Nc = C; p.rows_per_tap = 2 * C; p.k = k; p.kb_n = (C + bk - 1) / bk;
+    p.T = T; p.B = B; p.Kc = C; p.Nc = C; p.rows_per_tap = 2 * C; p.k = k; p.kb_n = (C + 31) / 32;
     fill_taps_tc(p.tap_off, k, dilation, causal, false);
     p.bias = bias; p.spk = spk; p.res = res; p.y = y; p.save_a = save_a; p.save_s = save_s;
     p.gate_mode = mode; p.residual = residual;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DV3_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
-    dim3 grid(t_tiles, C / br, B);
-    cudaStream_t st = (cudaStream_t)stream;
-    // CTA pairs (cta_group::2): two batches per M = 256 MMA, weights fetched once per pair
-    if (bk == 32 && cl == 1 && pair_usable(B, k, p.tap_off, (long long)t_tiles * (C / 64) * B)) {
+    const long long tiles64 = (long long)t_tiles * (C / 64) * B;
+
+    if (cl == 1 && pair_usable(B, k, p.tap_off, tiles64)) {            // opt-in: CTA pairs (cta_group::2)
         const PairGeom g = pair_geom(k, p.tap_off);
-        for (int pl = 0; pl < 2; ++pl) {
-            if (encode_tmap_bf16_3d(&maps.a[pl], plane(xd, pl, (long long)B * T * C), C, T, B, (uint64_t)C * 2,
-                                    (uint64_t)T * C * 2, bk, g.a_rows)) return 1;
-            if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
-                                    (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 64)) return 1;
-        }
+        if (enc(32, g.a_rows, 64)) return 1;
         return launch_tc_pair<TC_GATED>(maps, p, g, t_tiles, C / 64, B, st, "tc_convblock_fwd(pair)");
     }
-    // k > 1: the tap-reuse kernel (activation rows fetched once per 32-channel slice instead of once per tap)
-    if (bk == 32 && cl == 1 && taps_usable<2, 64>(k, p.tap_off, (long long)t_tiles * (C / 64) * B)) {
+    if (cl == 1 && taps_usable<2, 64>(k, p.tap_off, tiles64)) {        // opt-in: tap reuse (+ weight multicast)
         const TapGeom g = tap_geom<2, 64>(k, p.tap_off);
-        for (int pl = 0; pl < 2; ++pl) {
-            if (encode_tmap_bf16_3d(&maps.a[pl], plane(xd, pl, (long long)B * T * C), C, T, B, (uint64_t)C * 2,
-                                    (uint64_t)T * C * 2, bk, g.a_rows)) return 1;
-            if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
-                                    (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 64)) return 1;
-        }
+        if (enc(32, g.a_rows, 64)) return 1;
         if (taps_mcast(B)) return launch_tc_taps<TC_GATED, 2, 64, 2>(maps, p, g, t_tiles, C / 64, B, st, "tc_convblock_fwd(taps,mcast)");
         return launch_tc_taps<TC_GATED, 2, 64>(maps, p, g, t_tiles, C / 64, B, st, "tc_convblock_fwd(taps)");
     }
-    // more tiles than SMs: the persistent kernel (64 a | 64 b columns per tile, double-buffered accumulators)
-    if (tc_persist() && bk == 32 && cl == 1 && (long long)t_tiles * (C / 64) * B > 148) {
-        if (encode_tmap_bf16_3d(&maps.b[0], plane(w, 0, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
-                                (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 64)) return 1;
-        if (encode_tmap_bf16_3d(&maps.b[1], plane(w, 1, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
-                                (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 64)) return 1;
-        return launch_tc_persist<TC_GATED, 2, 64>(maps, p, t_tiles, C / 64, B, st, "tc_convblock_fwd(persistent)");
+    if (cl == 1 && tc_persist() && tiles64 > 148) {                    // persistent, double-buffered accumulators
+        if (persist_bk() == 64) {
+            p.kb_n = C / 64;
+            if (enc(64, 128, 64)) return 1;
+            return launch_tc_persist<TC_GATED, 2, 64, 64>(maps, p, t_tiles, C / 64, B, st, "tc_convblock_fwd(persistent)");
+        }
+        if (enc(32, 128, 64)) return 1;
+        return launch_tc_persist<TC_GATED, 2, 64>(maps, p, t_tiles, C / 64, B, st, "tc_convblock_fwd(persistent,bk32)");
     }
-    if (half) return launch_tc<TC_GATED, 2, 32, 2, 1, 64>(maps, p, grid, st, "tc_convblock_fwd(64)");
-    if (bk == 64) return launch_tc<TC_GATED, 2, 64, 2>(maps, p, grid, st, "tc_convblock_fwd");
+    static int force_half = -1, no_narrow = -1;
+    if (force_half < 0) { const char* e = getenv("DV3_TC_FORCE_HALF"); force_half = (e && atoi(e) == 1) ? 1 : 0; }
+    if (no_narrow < 0) { const char* e = getenv("DV3_TC_NO_NARROW"); no_narrow = (e && atoi(e) == 1) ? 1 : 0; }
+    // 64-channel tiles (64 a | 64 b columns) when 128-channel tiles would leave most of the 148 SMs idle
+    const bool half = cl == 1 && !no_narrow && (force_half || (long long)t_tiles * (C / 128) * B < 100);
+    if (half) {
+        dim3 grid(t_tiles, C / 64, B);
+        if (small_bk() == 64) {
+            p.kb_n = C / 64;
+            if (enc(64, 128, 64)) return 1;
+            return launch_tc<TC_GATED, 2, 64, 2, 1, 64>(maps, p, grid, st, "tc_convblock_fwd(64)");
+        }
+        if (enc(32, 128, 64)) return 1;
+        return launch_tc<TC_GATED, 2, 32, 2, 1, 64>(maps, p, grid, st, "tc_convblock_fwd(64,bk32)");
+    }
+    const int bk = tc_bk();
+    p.kb_n = (C + bk - 1) / bk;
+    if (enc(bk, 128, 128)) return 1;
+    if (cl > 1) {
+        for (int pl = 0; pl < 2; ++pl)
+            if (encode_tmap_bf16_3d(&maps.bs[pl], plane(w, pl, (long long)k * 2 * C * C), C, (uint64_t)k * 2 * C, 1,
+                                    (uint64_t)C * 2, (uint64_t)k * 2 * C * C * 2, bk, 128 / cl)) return 1;
+    }
+    dim3 grid(t_tiles, C / 128, B);
+    if (bk == 64) return launch_tc<TC_GATED, 2, 64, 2>(maps, p, grid, st, "tc_convblock_fwd(128,bk64)");
     if (cl == 4) return launch_tc<TC_GATED, 2, 32, 2, 4>(maps, p, grid, st, "tc_convblock_fwd(cluster4)");
     if (cl == 2) return launch_tc<TC_GATED, 2, 32, 2, 2>(maps, p, grid, st, "tc_convblock_fwd(cluster2)");
-    return launch_tc<TC_GATED, 2, 32, 2>(maps, p, grid, st, "tc_convblock_fwd");
+    return launch_tc<TC_GATED, 2, 32, 2>(maps, p, grid, st, "tc_convblock_fwd(128)");
 }
 
 // Generic conv / data-gradient:  out (B, Nc, T) fp32 = sum_j A[b, t+off_j, :] . W[j, n, :]  (+ epilogue)
-//   a: [npl][B][T][Kp] bf16 planes, Kp = Kc rounded up to 8;  w: [npl][k][Nc][Kp] bf16 planes; npl = 2 | 3.
+//   a: [npl][B][T][Kp] bf16 planes, Kp = Kc rounded up to 8;  w: [npl][k][Nc][Kp] bf16 planes; npl = 2.
 //   transpose_taps = 1 for a data gradient (offsets padl - j*d), 0 for a forward conv.
+// Same kernel selection as dv3_tc_convblock_fwd; BK = 64 needs Kc % 64 == 0 (else BK = 32: the 80-channel mel input).
 int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc, int Nc, int T, int k, int dilation,
                 int causal, int transpose_taps, const float* bias, int relu, float p_drop,
                 const unsigned long long* seed_ptr, unsigned salt, int addmode, const float* e1, const float* e2,
@@ -1253,86 +1287,100 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
     DV3_REQUIRE(k >= 1 && k <= MAX_TAPS_TC && (k == 1 || Nc % 128 == 0) && B <= 65535,
                 "tc_conv: unsupported shape B=%d Kc=%d Nc=%d T=%d k=%d", B, Kc, Nc, T, k);
     DV3_REQUIRE(npl == 2, "tc_conv: npl must be 2");
-    const int bk = tc_bk();
     const int Kp = (Kc + 7) / 8 * 8;
     TcMaps maps;
     const int cl = pick_cluster(B);
     const int t_tiles = (T + 127) / 128;
-    // tile width: two 128-column boxes only when that still fills the machine; 64 columns for small problems
-    const bool wide = Nc > 128 && (long long)t_tiles * ((Nc + 255) / 256) * B >= 120;
-    static int no_narrow = -1;
-    if (no_narrow < 0) { const char* e = getenv("DV3_TC_NO_NARROW"); no_narrow = (e && atoi(e) == 1) ? 1 : 0; }
-    const bool narrow = !wide && !no_narrow && bk == 32 && cl == 1 && Nc > 64 && (k == 1 || Nc % 64 == 0) &&
-                        (long long)t_tiles * ((Nc + 127) / 128) * B < 100;
-    const int br = narrow ? 64 : 128;
-    for (int pl = 0; pl < npl; ++pl) {
-        if (encode_tmap_bf16_3d(&maps.a[pl], plane(a, pl, (long long)B * T * Kp), Kc, T, B, (uint64_t)Kp * 2,
-                                (uint64_t)T * Kp * 2, bk, 128)) return 1;
-        if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
-                                (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, br)) return 1;
-        if (cl > 1 && encode_tmap_bf16_3d(&maps.bs[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
-                                          (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, 128 / cl)) return 1;
-    }
+    cudaStream_t st = (cudaStream_t)stream;
+    auto enc = [&](int bkx, int a_rows, int b_rows) -> int {
+        for (int pl = 0; pl < 2; ++pl) {
+            if (encode_tmap_bf16_3d(&maps.a[pl], plane(a, pl, (long long)B * T * Kp), Kc, T, B, (uint64_t)Kp * 2,
+                                    (uint64_t)T * Kp * 2, bkx, a_rows)) return 1;
+            if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
+                                    (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bkx, b_rows)) return 1;
+        }
+        return 0;
+    };
     TcParams p = {};
-    p.T = T; p.B = B; p.Kc = Kc; p.Nc = Nc; p.rows_per_tap = Nc; p.k = k; p.kb_n = (Kc + bk - 1) / bk;
+    p.T = T; p.B = B; p.Kc = Kc; p.Nc = Nc; p.rows_per_tap = Nc; p.k = k; p.kb_n = (Kc + 31) / 32;
     fill_taps_tc(p.tap_off, k, dilation, causal, transpose_taps != 0);
     p.out = out; p.bias = bias; p.relu = relu; p.e1 = e1; p.e2 = e2; p.alpha = alpha; p.addmode = addmode;
     p.p_drop = p_drop; p.seed_ptr = seed_ptr; p.salt = salt;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DV3_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
-    cudaStream_t st = (cudaStream_t)stream;
-    if (bk == 32 && cl == 1 && Nc % 128 == 0 && pair_usable(B, k, p.tap_off, (long long)t_tiles * (Nc / 128) * B)) {
+    static int no_narrow = -1;
+    if (no_narrow < 0) { const char* e = getenv("DV3_TC_NO_NARROW"); no_narrow = (e && atoi(e) == 1) ? 1 : 0; }
+    const long long tiles128 = (long long)t_tiles * ((Nc + 127) / 128) * B;
+    // tile width: two 128-column boxes only when that still fills the machine; 64 columns for small problems
+    const bool wide = Nc > 128 && (long long)t_tiles * ((Nc + 255) / 256) * B >= 120;
+    const bool narrow = !wide && !no_narrow && cl == 1 && Nc > 64 && (k == 1 || Nc % 64 == 0) && tiles128 < 100;
+    const bool k64 = Kc % 64 == 0;
+
+    if (cl == 1 && Nc % 128 == 0 && pair_usable(B, k, p.tap_off, tiles128)) {       // opt-in: CTA pairs
         const PairGeom g = pair_geom(k, p.tap_off);
-        for (int pl = 0; pl < 2; ++pl) {
-            if (encode_tmap_bf16_3d(&maps.a[pl], plane(a, pl, (long long)B * T * Kp), Kc, T, B, (uint64_t)Kp * 2,
-                                    (uint64_t)T * Kp * 2, bk, g.a_rows)) return 1;
-            if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
-                                    (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, 64)) return 1;
-        }
+        if (enc(32, g.a_rows, 64)) return 1;
         return launch_tc_pair<TC_CONV>(maps, p, g, t_tiles, Nc / 128, B, st, "tc_conv(pair)");
     }
-    if (bk == 32 && cl == 1 && k > 1) {
-        // k-tap conv / data gradient: tap-reuse kernel, 64-column tiles when 128-column ones cannot fill the machine
-        const bool n64 = narrow && !((long long)t_tiles * ((Nc + 127) / 128) * B > 148);
+    if (cl == 1 && k > 1) {                                                          // opt-in: tap reuse
+        const bool n64 = narrow && !(tiles128 > 148);
         const bool ok = n64 ? taps_usable<1, 64>(k, p.tap_off, (long long)t_tiles * (Nc / 64) * B)
-                            : taps_usable<1, 128>(k, p.tap_off, (long long)t_tiles * (Nc / 128) * B);
+                            : taps_usable<1, 128>(k, p.tap_off, tiles128);
         if (ok) {
             const TapGeom g = n64 ? tap_geom<1, 64>(k, p.tap_off) : tap_geom<1, 128>(k, p.tap_off);
-            for (int pl = 0; pl < 2; ++pl) {
-                if (encode_tmap_bf16_3d(&maps.a[pl], plane(a, pl, (long long)B * T * Kp), Kc, T, B, (uint64_t)Kp * 2,
-                                        (uint64_t)T * Kp * 2, bk, g.a_rows)) return 1;
-                if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
-                                        (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, n64 ? 64 : 128)) return 1;
-            }
+            if (enc(32, g.a_rows, n64 ? 64 : 128)) return 1;
             if (n64) return launch_tc_taps<TC_CONV, 1, 64>(maps, p, g, t_tiles, Nc / 64, B, st, "tc_conv(taps64)");
             if (taps_mcast(B)) return launch_tc_taps<TC_CONV, 1, 128, 2>(maps, p, g, t_tiles, Nc / 128, B, st, "tc_conv(taps,mcast)");
             return launch_tc_taps<TC_CONV, 1, 128>(maps, p, g, t_tiles, Nc / 128, B, st, "tc_conv(taps)");
         }
     }
-    if (tc_persist() && bk == 32 && cl == 1 && (long long)t_tiles * ((Nc + 127) / 128) * B > 148) {
+    if (cl == 1 && tc_persist() && tiles128 > 148) {
         // more 128-column tiles than SMs: persistent kernel with double-buffered accumulators
-        if (br != 128) {
-            for (int pl = 0; pl < 2; ++pl)
-                if (encode_tmap_bf16_3d(&maps.b[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
-                                        (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, 128)) return 1;
+        if (persist_bk() == 64 && k64) {
+            p.kb_n = Kc / 64;
+            if (enc(64, 128, 128)) return 1;
+            return launch_tc_persist<TC_CONV, 1, 128, 64>(maps, p, t_tiles, (Nc + 127) / 128, B, st, "tc_conv(persistent)");
         }
-        return launch_tc_persist<TC_CONV, 1, 128>(maps, p, t_tiles, (Nc + 127) / 128, B, st, "tc_conv(persistent)");
+        if (enc(32, 128, 128)) return 1;
+        return launch_tc_persist<TC_CONV, 1, 128>(maps, p, t_tiles, (Nc + 127) / 128, B, st, "tc_conv(persistent,bk32)");
     }
     if (narrow) {
         dim3 grid(t_tiles, (Nc + 63) / 64, B);
-        return launch_tc<TC_CONV, 1, 32, 2, 1, 64>(maps, p, grid, st, "tc_conv(64)");
+        if (small_bk() == 64 && k64) {
+            p.kb_n = Kc / 64;
+            if (enc(64, 128, 64)) return 1;
+            return launch_tc<TC_CONV, 1, 64, 2, 1, 64>(maps, p, grid, st, "tc_conv(64)");
+        }
+        if (enc(32, 128, 64)) return 1;
+        return launch_tc<TC_CONV, 1, 32, 2, 1, 64>(maps, p, grid, st, "tc_conv(64,bk32)");
     }
     if (wide) {
+        const int bk = tc_bk();
+        p.kb_n = (Kc + bk - 1) / bk;
+        if (enc(bk, 128, 128)) return 1;
+        if (cl > 1) {
+            for (int pl = 0; pl < 2; ++pl)
+                if (encode_tmap_bf16_3d(&maps.bs[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
+                                        (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, 128 / cl)) return 1;
+        }
         dim3 grid(t_tiles, (Nc + 255) / 256, B);
-        if (bk == 64) return launch_tc<TC_CONV, 2, 64, 2>(maps, p, grid, st, "tc_conv");
+        if (bk == 64) return launch_tc<TC_CONV, 2, 64, 2>(maps, p, grid, st, "tc_conv(256,bk64)");
         if (cl == 4) return launch_tc<TC_CONV, 2, 32, 2, 4>(maps, p, grid, st, "tc_conv(cluster4)");
         if (cl == 2) return launch_tc<TC_CONV, 2, 32, 2, 2>(maps, p, grid, st, "tc_conv(cluster2)");
-        return launch_tc<TC_CONV, 2, 32, 2>(maps, p, grid, st, "tc_conv");
+        return launch_tc<TC_CONV, 2, 32, 2>(maps, p, grid, st, "tc_conv(256)");
+    }
+    // one 128-column tile per CTA
+    const int bk = (cl == 1 && small_bk() == 64 && k64) ? 64 : tc_bk();
+    p.kb_n = (Kc + bk - 1) / bk;
+    if (enc(bk, 128, 128)) return 1;
+    if (cl > 1) {
+        for (int pl = 0; pl < 2; ++pl)
+            if (encode_tmap_bf16_3d(&maps.bs[pl], plane(w, pl, (long long)k * Nc * Kp), Kc, (uint64_t)k * Nc, 1,
+                                    (uint64_t)Kp * 2, (uint64_t)k * Nc * Kp * 2, bk, 128 / cl)) return 1;
     }
     dim3 grid(t_tiles, (Nc + 127) / 128, B);
-    if (bk == 64) return launch_tc<TC_CONV, 1, 64, 2>(maps, p, grid, st, "tc_conv");
+    if (bk == 64) return launch_tc<TC_CONV, 1, 64, 2>(maps, p, grid, st, "tc_conv(128)");
     if (cl == 4) return launch_tc<TC_CONV, 1, 32, 2, 4>(maps, p, grid, st, "tc_conv(cluster4)");
     if (cl == 2) return launch_tc<TC_CONV, 1, 32, 2, 2>(maps, p, grid, st, "tc_conv(cluster2)");
-    return launch_tc<TC_CONV, 1, 32, 2>(maps, p, grid, st, "tc_conv");
+    return launch_tc<TC_CONV, 1, 32, 2>(maps, p, grid, st, "tc_conv(128,bk32)");
 }
 
 int dv3_tc_wgrad_nsplit(int B, int Mw, int Nw, int T, int k) {
