@@ -202,7 +202,7 @@ def convblock_roofline(dev, pk, pk_kind):
         xs = torch.empty(2, Bc, T, C, device=dev, dtype=bf)
         ops.lib.call("dv3_tc_split_input", ops._p(x), ops._p(xs), 2, None, Bc, C, T, k, d, 0, 0.0, None, 0,
                      ops._stream())
-        name = "tcgen05 gated ConvBlock forward (persistent tap-reuse tc_conv_taps_kernel<GATED>) via dv3_tc_convblock_fwd"
+        name = "tcgen05 gated ConvBlock forward (persistent tc_conv_persist_kernel<GATED, BK=64>) via dv3_tc_convblock_fwd"
 
         def launch():
             ops.lib.call("dv3_tc_convblock_fwd", ops._p(xs), ops._p(wfwd), 2, ops._p(bias), None, ops._p(x), ops._p(y),
