@@ -105,3 +105,57 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The three structs that cross the C ABI by pointer (Dv3WnEntry, Dv3IncStep, Dv3IncAttn) are mirrored by hand in
+    ctypes; compile the header with gcc and compare sizeof / every field offset."""
+    import ctypes
+    import os
+    import subprocess
+    from deepvoice3_pytorch_b200.weight_bank import Dv3WnEntry
+    from deepvoice3_pytorch_b200.incremental import Dv3IncStep, Dv3IncAttn
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"Dv3WnEntry": Dv3WnEntry, "Dv3IncStep": Dv3IncStep, "Dv3IncAttn": Dv3IncAttn}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dv3b200.h"', 'int main(void) {']
+    for name, st in structs.items():
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (name, name))
+        for fname, _ in st._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (name, fname, name, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        name, field, value = line.split()
+        st = structs[name]
+        got = ctypes.sizeof(st) if field == "sizeof" else getattr(st, field).offset
+        assert got == int(value), "%s.%s: ctypes %d vs C %s" % (name, field, got, value)
+
+
+def test_incremental_stop_rule_matches_reference_loop():
+    """Host logic of the free-running decoder: the number of steps derived from the done flags equals what the
+    reference's while-loop does (break after step n if all(done > .5) and n > min_steps, or n > max_steps;
+    deepvoice3.py:466-470)."""
+    import torch
+    from deepvoice3_pytorch_b200.incremental import _stop_step
+
+    def reference(done, min_steps, max_steps):
+        t = 0
+        while t < done.size(1):
+            d = done[:, t]
+            t += 1
+            if bool((d > 0.5).all()) and t > min_steps:
+                return t
+            elif t > max_steps:
+                return t
+        return None
+
+    gen = torch.Generator().manual_seed(0)
+    for _ in range(200):
+        n = int(torch.randint(1, 40, (1,), generator=gen))
+        done = torch.rand(3, n, generator=gen) ** 0.2
+        mn, mx = int(torch.randint(0, 12, (1,), generator=gen)), int(torch.randint(5, 45, (1,), generator=gen))
+        assert _stop_step(done, mn, mx) == reference(done, mn, mx)
