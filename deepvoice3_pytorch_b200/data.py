@@ -4,6 +4,10 @@ padding rules, and a distributed variant of its length-bucketed sampler.
 * ``collate`` restates reference train.py:293-360 (``collate_fn``) plus the per-step slicing the train loop applies
   (mel[:, 0::downsample_step], train.py:639-640) and returns the dict ``TrainStep.step`` consumes (optionally in
   pinned memory so the H2D copies are asynchronous).
+* ``TrainTxtDataset`` reads the on-disk format ``preprocess.py`` writes (``train.txt`` with one
+  ``spec.npy|mel.npy|n_frames|text[|speaker_id]`` line per utterance, preprocess.py:27-30; the three reference data
+  sources TextDataSource / MelSpecDataSource / LinearSpecDataSource + PyTorchDataset, train.py:96-257, in one class).
+  The text frontend (string -> token ids) stays the caller's: pass the reference's ``frontend.text_to_sequence``.
 * ``DistributedSimilarLengthSampler`` restates ``PartialyRandomizedSimilarTimeLengthSampler`` (train.py:195-239):
   sort by length, shuffle inside groups of ``batch_group_size``, permute whole mini-batches -- then deals the
   mini-batches round-robin to the ranks, so every rank sees disjoint batches of similar length (what the
@@ -62,6 +66,43 @@ def collate(batch, r=1, downsample_step=4, pin=False):
         out = {k: v.pin_memory() for k, v in out.items()}
     out["input_lengths"] = np.asarray(input_lengths, dtype=np.int64)
     return out
+
+
+class TrainTxtDataset(torch.utils.data.Dataset):
+    """Items are what ``collate`` consumes: (token ids int32, mel (T, num_mels) float32, linear (T, n_freq) float32
+    [, speaker_id]).  ``frame_lengths`` (column 3 of train.txt) feeds the length-bucketed sampler without touching
+    the .npy files.  ``speaker_id`` filters a multi-speaker corpus down to one speaker (and then yields 3-tuples),
+    like the reference data sources do (train.py:101-122, 169-177)."""
+
+    def __init__(self, data_root, text_to_sequence, speaker_id=None, mmap=True):
+        import os
+        self.data_root, self.text_to_sequence, self.mmap = data_root, text_to_sequence, mmap
+        with open(os.path.join(data_root, "train.txt"), "rb") as f:
+            rows = [line.decode("utf-8").rstrip("\n").split("|") for line in f if line.strip()]
+        if not rows:
+            raise ValueError("empty train.txt under %s" % data_root)
+        n = len(rows[0])
+        if n not in (4, 5) or any(len(r) != n for r in rows):
+            raise ValueError("train.txt lines must have 4 or 5 '|'-separated fields")
+        self.multi_speaker = n == 5
+        if self.multi_speaker and speaker_id is not None:
+            rows = [r for r in rows if int(r[4]) == speaker_id]
+            self.multi_speaker = False
+        self.rows = rows
+        self.frame_lengths = [int(r[2]) for r in rows]
+
+    def __len__(self):
+        return len(self.rows)
+
+    def _load(self, name):
+        import os
+        return np.load(os.path.join(self.data_root, name), mmap_mode="r" if self.mmap else None)
+
+    def __getitem__(self, idx):
+        r = self.rows[idx]
+        seq = np.asarray(self.text_to_sequence(r[3]), dtype=np.int32)
+        item = (seq, np.asarray(self._load(r[1]), dtype=np.float32), np.asarray(self._load(r[0]), dtype=np.float32))
+        return item + (int(r[4]),) if self.multi_speaker else item
 
 
 class DistributedSimilarLengthSampler(torch.utils.data.Sampler):

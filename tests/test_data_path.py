@@ -66,3 +66,45 @@ def test_distributed_sampler_partitions_batches():
     s = DistributedSimilarLengthSampler(lengths, batch_size=bs, batch_group_size=64, rank=0, world_size=world, seed=5)
     s.set_epoch(4)
     assert list(iter(s)) != per_rank[0]
+
+
+def test_train_txt_dataset_reads_the_preprocess_format(tmp_path):
+    """The on-disk format of the reference's preprocess.py (train.txt + .npy pairs, preprocess.py:27-30 /
+    ljspeech.py:72-76) through TrainTxtDataset -> sampler -> collate, single- and multi-speaker, with the speaker
+    filter of the reference data sources (train.py:101-122)."""
+    import numpy as np
+    import torch
+    from deepvoice3_pytorch_b200.data import TrainTxtDataset, DistributedSimilarLengthSampler, collate
+    rng = np.random.RandomState(0)
+    lines, specs = [], {}
+    for i in range(12):
+        n = int(rng.randint(9, 40))
+        spec = rng.rand(n, 33).astype(np.float32)
+        mel = rng.rand(n, 80).astype(np.float32)
+        np.save(tmp_path / ("spec-%05d.npy" % i), spec)
+        np.save(tmp_path / ("mel-%05d.npy" % i), mel)
+        text = "utt %d %s" % (i, "a" * int(rng.randint(1, 9)))
+        lines.append("spec-%05d.npy|mel-%05d.npy|%d|%s|%d" % (i, i, n, text, i % 3))
+        specs[i] = (spec, mel, text)
+    (tmp_path / "train.txt").write_text("\n".join(lines) + "\n", encoding="utf-8")
+
+    def text_to_sequence(t):
+        return [ord(c) % 100 + 2 for c in t] + [1]
+
+    ds = TrainTxtDataset(str(tmp_path), text_to_sequence)
+    assert len(ds) == 12 and ds.multi_speaker and ds.frame_lengths == [specs[i][0].shape[0] for i in range(12)]
+    seq, mel, lin, spk = ds[5]
+    assert spk == 2 and seq.dtype == np.int32 and list(seq) == text_to_sequence(specs[5][2])
+    np.testing.assert_array_equal(mel, specs[5][1])
+    np.testing.assert_array_equal(lin, specs[5][0])
+    one = TrainTxtDataset(str(tmp_path), text_to_sequence, speaker_id=1)
+    assert len(one) == 4 and not one.multi_speaker and len(one[0]) == 3
+    sampler = DistributedSimilarLengthSampler(ds.frame_lengths, batch_size=4, rank=0, world_size=1, seed=3)
+    loader = torch.utils.data.DataLoader(ds, batch_size=4, sampler=sampler, drop_last=True,
+                                         collate_fn=lambda b: collate(b, r=1, downsample_step=4))
+    seen = 0
+    for batch in loader:
+        assert batch["x"].shape[0] == 4 and batch["y"].shape[-1] == 33 and batch["mel"].shape[-1] == 80
+        assert batch["y"].shape[1] == 4 * batch["mel"].shape[1] and "speaker_ids" in batch
+        seen += 4
+    assert seen == 12
