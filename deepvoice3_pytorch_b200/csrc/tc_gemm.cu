@@ -860,6 +860,166 @@ tc_conv_pair_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
     if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair kernel with 128-byte operand rows and one (tap, 64-channel slice) per stage -- the round-2 candidate
+// (opt-in: DV3_TC_PAIR64=1 when there are more tiles than SMs, =2 whenever the batch is even).
+// Why: the decomposition experiments put the MMA stream itself at 75 % of nominal -- a fixed
+// ~30 clk per tcgen05.mma on top of 128 / 64 clk of math for the N = 256 / N = 128 instructions of the split-bf16
+// scheme.  cta_group::2 doubles the work per instruction (M = 256) at the same fixed cost and halves the weight bytes
+// per SM; the first pair kernel above showed neither effect because it also carried the BK = 32 rows (twice the TMA
+// operations per byte) and the row-shifted tap-reuse descriptors (MMAs 18 % slower).  This variant keeps the pair
+// protocol of tc_conv_pair_kernel (validated bit-for-bit) and changes only the stage geometry:
+//     stage (56 KB, 4 deep) = A: 2 planes x 128 rows x 128 B   |   B: [plane r: 128 rows][p0 rows 64r..64r+63] x 128 B
+// STATUS: compiles; NOT yet run on a GPU (round 1 ran out of GPU minutes) -- default off, first item of round 2.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_conv_pair64_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p, int tiles_x,
+                      int tiles_y, int num_tiles) {
+    constexpr int BK = 64, NCOLS = 128;
+    constexpr int A_PLANE = 128 * BK * 2;               // 16 KB
+    constexpr int B_OFF = 2 * A_PLANE;
+    // weights per stage: [this CTA's half of (p0 ; p1): two 64-row boxes = B_Y bytes][its half of p0: one box = B_X]
+    constexpr int B_Y = 128 * BK * 2, B_X = 64 * BK * 2;
+    constexpr int STAGE = B_OFF + B_Y + B_X;            // 56 KB
+    constexpr int STAGES = (SMEM_LIMIT - 2048) / STAGE; // 4
+    static_assert(STAGES >= 2, "pipeline needs at least two stages");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_iters = p.k * p.kb_n;                   // kb_n = 64-channel slices per tap
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.a[1]); prefetch_tmap(&maps.b[0]); prefetch_tmap(&maps.b[1]);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_alloc_pair<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto decode = [&](int tile, int& a_row0, int& a_z, int& b_row0, int& b_row1) {
+        const int ty = tile % tiles_y, r = tile / tiles_y;
+        const int tx = r % tiles_x;
+        a_z = 2 * (r / tiles_x) + (int)rank;
+        a_row0 = tx * 128;
+        if (MODE == TC_GATED) { b_row0 = ty * 64; b_row1 = p.Nc + ty * 64; }
+        else { b_row0 = ty * 128; b_row1 = b_row0 + 64; }
+    };
+
+    if (warp == 0 && lane == 0) {
+        int it = 0;
+        constexpr uint32_t stage_tx = 2u * (uint32_t)STAGE;               // both CTAs' bytes
+        for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+            int a_row0, a_z, b_row0, b_row1;
+            decode(tile, a_row0, a_z, b_row0, b_row1);
+            for (int kit = 0; kit < n_iters; ++kit, ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait_cluster(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * STAGE;
+                const int j = kit / p.kb_n, kb = kit - j * p.kb_n;
+                const int ax = kb * BK, ay = a_row0 + p.tap_off[j];
+                const int r0 = j * p.rows_per_tap + b_row0, r1 = j * p.rows_per_tap + b_row1;
+                if (rank == 0) mbar_arrive_expect_tx(&full[s], stage_tx);
+                const uint32_t lead_full = mapa_u32(&full[s], 0);
+                tma_load_3d_pair(st, &maps.a[0], lead_full, ax, ay, a_z);
+                tma_load_3d_pair(st + A_PLANE, &maps.a[1], lead_full, ax, ay, a_z);
+                uint8_t* bd = st + B_OFF;
+                tma_load_3d_pair(bd, &maps.b[rank], lead_full, ax, r0, 0);              // plane `rank`, box 0
+                tma_load_3d_pair(bd + B_X, &maps.b[rank], lead_full, ax, r1, 0);        // plane `rank`, box 1
+                tma_load_3d_pair(bd + B_Y, &maps.b[0], lead_full, ax, rank == 0 ? r0 : r1, 0);   // p0, box `rank`
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        constexpr uint32_t idesc1 = make_idesc_bf16(256, 2 * NCOLS), idesc2 = make_idesc_bf16(256, NCOLS);
+        int it = 0, tcount = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++tcount) {
+            const int a = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait_cluster(&tempty[a], aph ^ 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + a * 2 * NCOLS;
+            for (int kit = 0; kit < n_iters; ++kit, ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait_cluster(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE);
+                const uint64_t da0 = make_desc<BK>(sa), da1 = make_desc<BK>(sa + A_PLANE);
+                const uint64_t dby = make_desc<BK>(sa + B_OFF), dbx = make_desc<BK>(sa + B_OFF + B_Y);
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; ++kk) {
+                    const uint64_t adv = (uint64_t)(kk * 2);
+                    if (p.debug & 2) continue;
+                    umma_bf16_pair(acc, da0 + adv, dby + adv, idesc1, (kit | kk) != 0);   // p0 x [p0 ; p1]
+                    umma_bf16_pair(acc + NCOLS, da1 + adv, dbx + adv, idesc2, 1);         // p1 x p0
+                }
+                umma_commit_pair(&empty[s]);
+            }
+            umma_commit_pair(&tfull[a]);
+        }
+    } else if (warp >= 2) {
+        const int q = warp & 3, row = q * 32 + lane;
+        int tcount = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++tcount) {
+            int a_row0, a_z, b_row0, b_row1;
+            decode(tile, a_row0, a_z, b_row0, b_row1);
+            const int a = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait_cluster(&tfull[a], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + a * 2 * NCOLS + ((uint32_t)(q * 32) << 16);
+            if (!(p.debug & 1)) {
+                if (MODE == TC_GATED) epilogue_gated<64, NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+                else epilogue_conv<NCOLS>(p, taddr, a_row0, a_z, b_row0, row);
+            }
+            tc_fence_before();
+            if (rank == 0) mbar_arrive(&tempty[a]);
+            else mbar_arrive_remote(&tempty[a], 0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
+}
+
+static bool pair64_usable(int B, int Kc, long long num_tiles) {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("DV3_TC_PAIR64"); mode = e ? atoi(e) : 0; }
+    return mode > 0 && (B & 1) == 0 && Kc % 64 == 0 && (mode > 1 || num_tiles > 148);
+}
+
+template <int MODE>
+static int launch_tc_pair64(const TcMaps& maps, const TcParams& p, int tiles_x, int tiles_y, int batch,
+                            cudaStream_t st, const char* what) {
+    constexpr int STAGE = 2 * 128 * 64 * 2 + 128 * 64 * 2 + 64 * 64 * 2;
+    constexpr int SMEM = ((SMEM_LIMIT - 2048) / STAGE) * STAGE + 1024 + 512;
+    static bool configured = false;
+    auto kern = tc_conv_pair64_kernel<MODE>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) { set_error("%s: cannot set %d B dynamic smem: %s", what, SMEM, cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int num_tiles = tiles_x * tiles_y * (batch / 2);
+    int clusters = sms / 2;
+    if (num_tiles < clusters) clusters = num_tiles;
+    kern<<<2 * clusters, TC_THREADS, SMEM, st>>>(maps, p, tiles_x, tiles_y, num_tiles);
+    return check_launch(what);
+}
+
 static int g_pair = -1;
 static int tc_pair() {                     // DV3_TC_PAIR: 0 = off, 1 = when there are more tiles than SMs, 2 = whenever possible
     if (g_pair < 0) { const char* e = getenv("DV3_TC_PAIR"); g_pair = e ? atoi(e) : 0; }
@@ -1226,6 +1386,11 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DV3_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     const long long tiles64 = (long long)t_tiles * (C / 64) * B;
 
+    if (cl == 1 && pair64_usable(B, C, tiles64)) {                     // opt-in, unvalidated: CTA pairs, BK = 64
+        p.kb_n = C / 64;
+        if (enc(64, 128, 64)) return 1;
+        return launch_tc_pair64<TC_GATED>(maps, p, t_tiles, C / 64, B, st, "tc_convblock_fwd(pair64)");
+    }
     if (cl == 1 && pair_usable(B, k, p.tap_off, tiles64)) {            // opt-in: CTA pairs (cta_group::2)
         const PairGeom g = pair_geom(k, p.tap_off);
         if (enc(32, g.a_rows, 64)) return 1;
@@ -1315,6 +1480,11 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
     const bool narrow = !wide && !no_narrow && cl == 1 && Nc > 64 && (k == 1 || Nc % 64 == 0) && tiles128 < 100;
     const bool k64 = Kc % 64 == 0;
 
+    if (cl == 1 && Nc % 128 == 0 && pair64_usable(B, Kc, tiles128)) {               // opt-in, unvalidated
+        p.kb_n = Kc / 64;
+        if (enc(64, 128, 64)) return 1;
+        return launch_tc_pair64<TC_CONV>(maps, p, t_tiles, Nc / 128, B, st, "tc_conv(pair64)");
+    }
     if (cl == 1 && Nc % 128 == 0 && pair_usable(B, k, p.tap_off, tiles128)) {       // opt-in: CTA pairs
         const PairGeom g = pair_geom(k, p.tap_off);
         if (enc(32, g.a_rows, 64)) return 1;

@@ -28,6 +28,8 @@ for (B, C, T, k, d) in SHAPES:
     for e in prof.key_averages():
         if "tc_conv_kernel" in e.key:
             rows[e.key.split("tc_conv_kernel")[1][:18]] = e.device_time_total / e.count
+        elif "tc_conv_pair64" in e.key:
+            rows["pair64" + e.key.split("tc_conv_pair64_kernel")[1][:4]] = e.device_time_total / e.count
         elif "tc_conv_pair" in e.key:
             rows["pair" + e.key.split("tc_conv_pair_kernel")[1][:4]] = e.device_time_total / e.count
         elif "tc_conv_taps" in e.key:
