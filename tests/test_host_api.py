@@ -159,3 +159,46 @@ def test_incremental_stop_rule_matches_reference_loop():
         done = torch.rand(3, n, generator=gen) ** 0.2
         mn, mx = int(torch.randint(0, 12, (1,), generator=gen)), int(torch.randint(5, 45, (1,), generator=gen))
         assert _stop_step(done, mn, mx) == reference(done, mn, mx)
+
+
+def test_hparams_mapping_matches_the_bench_presets():
+    """hparams.builder_kwargs restates reference train.py:812-840; applied to the values of the reference's
+    presets/*.json (copied below: they are data) it must give exactly the builder kwargs bench.py hard-codes for the
+    BASELINE.json presets, and train_step_kwargs must give the optimiser / loss settings of train.py."""
+    import bench
+    from deepvoice3_pytorch_b200 import hparams
+    from deepvoice3_pytorch_b200.train_step import noam_learning_rate_decay
+    common = dict(adam_beta1=0.5, adam_beta2=0.9, adam_eps=1e-6, binary_divergence_weight=0.1, clip_thresh=0.1,
+                  converter_channels=256, decoder_channels=256, downsample_step=4, dropout=0.050000000000000044,
+                  fft_size=1024, force_monotonic_attention=True, freeze_embedding=False, initial_learning_rate=0.0005,
+                  kernel_size=3, lr_schedule="noam_learning_rate_decay", lr_schedule_kwargs={}, masked_loss_weight=0.5,
+                  num_mels=80, outputs_per_step=1, padding_idx=0, speaker_embed_dim=16,
+                  trainable_positional_encodings=False, use_decoder_state_for_postnet_input=True,
+                  use_guided_attention=True, use_memory_mask=True, window_ahead=3, window_backward=1,
+                  key_position_rate=1.385, query_position_rate=1.0, embedding_weight_std=0.1)
+    presets = {
+        "deepvoice3_ljspeech": dict(common, builder="deepvoice3", encoder_channels=512, text_embed_dim=256, n_speakers=1,
+                                    max_positions=512, speaker_embedding_weight_std=0.01, key_projection=True,
+                                    value_projection=True, guided_attention_sigma=0.2),
+        "nyanko_ljspeech": dict(common, builder="nyanko", encoder_channels=256, text_embed_dim=128, n_speakers=1,
+                                max_positions=512, speaker_embedding_weight_std=0.01, key_projection=False,
+                                value_projection=False, guided_attention_sigma=0.2),
+        "deepvoice3_vctk": dict(common, builder="deepvoice3_multispeaker", encoder_channels=512, text_embed_dim=256,
+                                n_speakers=108, max_positions=1024, speaker_embedding_weight_std=0.05,
+                                key_projection=True, value_projection=True, guided_attention_sigma=0.4,
+                                key_position_rate=7.6, query_position_rate=2.0),
+    }
+    for name, hp in presets.items():
+        bname, kw = hparams.builder_kwargs(hp, n_vocab=149)
+        want_name, want_kw, extra = bench.PRESETS[name]
+        assert bname == want_name
+        assert set(kw) == set(want_kw)
+        for k in kw:
+            assert kw[k] == pytest.approx(want_kw[k]), (name, k)
+        ts = hparams.train_step_kwargs(hp)
+        assert ts["guided_attention_sigma"] == extra["guided_attention_sigma"]
+        assert ts["betas"] == (0.5, 0.9) and ts["eps"] == 1e-6 and ts["clip_thresh"] == 0.1
+        assert ts["lr_schedule"] is noam_learning_rate_decay and ts["init_lr"] == 5e-4
+    model = hparams.build_model(dict(presets["nyanko_ljspeech"], encoder_channels=32, decoder_channels=32,
+                                     converter_channels=32, text_embed_dim=16), n_vocab=149)
+    assert model.seq2seq.decoder.in_dim == 80 and model.linear_dim == 513
