@@ -14,11 +14,22 @@
 //           (plain conv forward with bias/ReLU, and every data gradient: A = dY or dAB, W = transposed weight)
 //   WGRAD : D[m, n] (j)   = sum_{b,t}  dY[b, m, t] * Xs_j[b, n, t]                 M = 128 rows,       N = NBOX x 128
 //
-// All operands are K-major bf16 tiles of 128 rows x BK (BK = 32: 64-byte rows, SWIZZLE_64B; BK = 64: 128-byte rows,
-// SWIZZLE_128B) fetched by TMA; the conv's zero padding, the causal shift, ragged T / channel tails are TMA
-// out-of-bounds zero fill.  Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA
-// issuer, warps 2-5 = epilogue (TMEM -> registers -> fused gate / bias / mask / residual math -> stores coalesced
-// along T).
+// All operands are K-major bf16 tiles of 128 rows x BK (BK = 64: 128-byte rows, SWIZZLE_128B -- the default wherever
+// the channel count is a multiple of 64; BK = 32: 64-byte rows, SWIZZLE_64B) fetched by TMA; the conv's zero padding,
+// the causal shift, ragged T / channel tails are TMA out-of-bounds zero fill.  Warp roles (192 threads): warp 0 = TMA
+// producer, warp 1 = TMEM owner + single-thread MMA issuer, warps 2-5 = epilogue (TMEM -> registers -> fused gate /
+// bias / mask / residual math -> stores coalesced along T).
+//
+// Kernels in this file (selection logic + measurements at dv3_tc_convblock_fwd / dv3_tc_conv below):
+//   tc_conv_kernel          one output tile per CTA (small layers; 64- or 128-column tiles; optional weight multicast)
+//   tc_conv_persist_kernel  one CTA per SM walks the tile list, two accumulator sets in TMEM (epilogue of tile n
+//                           overlaps the MMAs of tile n+1)                                   <- default for big layers
+//   tc_conv_taps_kernel     persistent + activation rows fetched once per channel slice for all taps (opt-in)
+//   tc_conv_pair_kernel     persistent + CTA pairs, tcgen05 cta_group::2, M = 256 (opt-in); tc_conv_pair64_kernel
+//                           = its BK = 64 variant (round-2 candidate, not yet run)
+//   tc_wgrad_mn_kernel      weight gradient from MN-major operands
+// In every kernel the hi and lo weight planes sit back to back in the stage, so p0(A) x [p0(W) ; p1(W)] is ONE
+// N = 2*NCOLS MMA filling the main | cross accumulators, followed by p1(A) x p0(W) into the cross accumulator.
 #include "tc_common.cuh"
 
 namespace dv3 {
