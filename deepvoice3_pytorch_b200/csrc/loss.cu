@@ -23,11 +23,13 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 
 // y_hat (B, T, D) predictions, y (B, T, D) targets; pairs (y_hat[b,t], y[b,t+r]) for t < T-r; lengths int64 [B]
 // (valid target frames per utterance, in this tensor's time units); grad (B, T, D) fully written.
-//   loss += sum coef*((1-bw)*|d| + bw*z),  coef = w*m/Sm + (1-w)/N,  m = (t+r < len_b)
+//   loss += sum (1-bw)*coef1*|d| + bw*coef*z,  coef = w*m/Sm + (1-w)/N,  m = (t+r < len_b)
+// priority bins (train.py:559-567): the L1 term becomes (1-pw)*L1(all bins) + pw*L1(bins < pbin), i.e.
+//   coef1 = (1-pw)*coef + [d < pbin]*pw*coef*(D/pbin)     (the same masked/plain means over the pbin-wide slice)
 __global__ void spec_loss_kernel(const float* __restrict__ y_hat, const float* __restrict__ y,
                                  const long long* __restrict__ lengths, float* __restrict__ grad,
                                  float* __restrict__ loss, int B, int T, int D, int r, float w, float bw,
-                                 float eps) {
+                                 float eps, int pbin, float pw) {
     __shared__ float red[8];
     __shared__ float s_inv_sm;
     if (threadIdx.x == 0) {
@@ -45,6 +47,8 @@ __global__ void spec_loss_kernel(const float* __restrict__ y_hat, const float* _
     const float inv_n = 1.f / ((float)B * (float)(T - r) * (float)D);
     const long long total = (long long)B * T * D;
     const long long shift = (long long)r * D;
+    const bool prio = pbin > 0 && pw > 0.f;
+    const float prio_gain = prio ? pw * ((float)D / (float)pbin) : 0.f;
     float acc = 0.f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -56,8 +60,10 @@ __global__ void spec_loss_kernel(const float* __restrict__ y_hat, const float* _
             const float m = (t + r < lengths[b]) ? 1.f : 0.f;
             const float coef = w * m * inv_sm + (1.f - w) * inv_n;
             const float d = p - tg;
-            float e = (1.f - bw) * fabsf(d);
-            float de = (1.f - bw) * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+            float c1 = 1.f;                                   // L1 weight relative to coef
+            if (prio) c1 = (1.f - pw) + ((int)(i - bt * D) < pbin ? prio_gain : 0.f);
+            float e = c1 * (1.f - bw) * fabsf(d);
+            float de = c1 * (1.f - bw) * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
             if (bw > 0.f) {
                 const float L = logf(p + eps) - logf(1.f - p + eps);
                 const float u = expf(L);
@@ -118,12 +124,16 @@ using namespace dv3;
 extern "C" {
 
 int dv3_spec_loss(const float* y_hat, const float* y, const long long* lengths, float* grad, float* loss, int B,
-                  int T, int D, int r, float masked_loss_weight, float binary_divergence_weight, void* stream) {
+                  int T, int D, int r, float masked_loss_weight, float binary_divergence_weight, int priority_bin,
+                  float priority_weight, void* stream) {
     DV3_REQUIRE(T > r && r >= 0, "spec_loss: need T > r");
+    DV3_REQUIRE(priority_bin >= 0 && priority_bin <= D && priority_weight >= 0.f && priority_weight <= 1.f,
+                "spec_loss: priority_bin=%d (D=%d) priority_weight=%g out of range", priority_bin, D, priority_weight);
     long long blocks = ((long long)B * T * D + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     spec_loss_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(y_hat, y, lengths, grad, loss, B, T, D, r,
-                                                                   masked_loss_weight, binary_divergence_weight, 1e-8f);
+                                                                   masked_loss_weight, binary_divergence_weight, 1e-8f,
+                                                                   priority_bin, priority_weight);
     return check_launch("spec_loss");
 }
 

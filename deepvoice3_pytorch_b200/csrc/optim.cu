@@ -7,8 +7,15 @@
 
 namespace dv3 {
 
-// out[0] += sum(x^2)   (out must be zeroed by the caller; grid-stride, one atomic per block)
-__global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+// out[0] = sum(x^2), DETERMINISTIC: every block writes its partial to scratch[blockIdx.x]; the block that takes the
+// last ticket sums the partials in index order, so the result does not depend on the order blocks finish in -- all
+// data-parallel replicas (which hold bit-identical all-reduced gradients) get the same clip coefficient.
+// scratch: >= DV3_SUMSQ_SCRATCH floats; scratch[DV3_SUMSQ_SCRATCH-1] is the ticket counter (zero before first use;
+// the kernel leaves it zero).
+constexpr int SUMSQ_MAX_BLOCKS = 148 * 8;
+constexpr int SUMSQ_SCRATCH = 2048;
+__global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out,
+                             float* __restrict__ scratch) {
     float s = 0.f;
     const long long n4 = n >> 2;
     const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -21,13 +28,36 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __
          i += (long long)gridDim.x * blockDim.x)
         s = fmaf(x[i], x[i], s);
     __shared__ float red[32];
+    __shared__ bool last;
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x < 32) {
         s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
         s = warp_sum(s);
-        if (threadIdx.x == 0) atomicAdd(out, s);
+        if (threadIdx.x == 0) {
+            scratch[blockIdx.x] = s;
+            __threadfence();
+            unsigned* ticket = reinterpret_cast<unsigned*>(scratch + SUMSQ_SCRATCH - 1);
+            last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        }
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // fixed-order tree over the per-block partials: thread t sums partials t, t+256, ... then a block reduction
+    float t = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(&scratch[i]);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) {
+            out[0] = t;
+            *reinterpret_cast<unsigned*>(scratch + SUMSQ_SCRATCH - 1) = 0u;
+        }
     }
 }
 
@@ -60,12 +90,15 @@ using namespace dv3;
 
 extern "C" {
 
-int dv3_sumsq(const float* x, long long n, float* out, void* stream) {
+int dv3_sumsq_scratch_floats(void) { return SUMSQ_SCRATCH; }
+
+int dv3_sumsq(const float* x, long long n, float* out, float* scratch, void* stream) {
     DV3_REQUIRE(((uintptr_t)x & 15) == 0, "sumsq: pointer must be 16-byte aligned");
+    DV3_REQUIRE(scratch != nullptr, "sumsq: scratch buffer required");
     long long blocks = (n / 4 + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > SUMSQ_MAX_BLOCKS) blocks = SUMSQ_MAX_BLOCKS;
     if (blocks < 1) blocks = 1;
-    sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+    sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out, scratch);
     return check_launch("sumsq");
 }
 

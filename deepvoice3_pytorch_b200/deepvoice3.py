@@ -291,6 +291,7 @@ class Converter(nn.Module):
                            dropout=dropout))
         self.convolutions = nn.ModuleList(head + tail)
 
+    @ops.forward_scope
     def forward(self, x, speaker_embed=None):
         """x (B, T, in_dim) -> (B, T*upsampling, out_dim) (reference deepvoice3.py:582-604)."""
         assert self.n_speakers == 1 or speaker_embed is not None

@@ -51,6 +51,11 @@ def build_model(hp, n_vocab):
 
 def train_step_kwargs(hp):
     """Keyword arguments of ``TrainStep`` for this hyper-parameter set."""
+    # settings train.py reads that this step does not implement must not be dropped silently
+    if hp.get("weight_decay", 0.0) != 0.0 or hp.get("amsgrad", False):
+        raise ValueError("TrainStep's flat Adam implements torch.optim.Adam without weight_decay / amsgrad "
+                         "(reference train.py:975-979); got weight_decay=%r amsgrad=%r"
+                         % (hp.get("weight_decay"), hp.get("amsgrad")))
     schedule = hp.get("lr_schedule")
     if schedule is not None and not callable(schedule):
         base = getattr(_ts, schedule)          # reference: getattr(lrschedule, hparams.lr_schedule)
@@ -60,4 +65,5 @@ def train_step_kwargs(hp):
                 clip_thresh=hp["clip_thresh"], r=hp["outputs_per_step"], downsample_step=hp["downsample_step"],
                 masked_loss_weight=hp["masked_loss_weight"], binary_divergence_weight=hp["binary_divergence_weight"],
                 guided_attention_sigma=hp["guided_attention_sigma"], use_guided_attention=hp["use_guided_attention"],
-                lr_schedule=schedule)
+                priority_freq=hp.get("priority_freq", 3000), priority_freq_weight=hp.get("priority_freq_weight", 0.0),
+                sample_rate=hp.get("sample_rate", 22050), lr_schedule=schedule)

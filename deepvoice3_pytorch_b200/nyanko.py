@@ -139,5 +139,6 @@ class Converter(nn.Module):
             c1(Fd, Fd, 2.0), nn.Sigmoid(),
         )
 
+    @ops.forward_scope
     def forward(self, x, speaker_embed=None):
         return ops.transpose12(run_conv_stack(self.convnet, ops.transpose12(x)))

@@ -52,23 +52,34 @@ def _c(t):
 class DropoutState:
     """Step seed in device memory + call-site salts.
 
-    keep(i) = f(seed[0], salt, i).  ``seed`` is an int64[1] device tensor: bump it once per training
-    step (``advance()`` is a device-side add, so it can live inside a captured CUDA graph); salts are
-    handed out in call order and must be reset at the start of every forward so that the backward (and
-    a graph replay) see the same sequence."""
+    keep(i) = f(seed[0], salt, i).  ``base`` is a persistent int64[1] device tensor that is bumped IN PLACE at the
+    start of every training forward (a device-side add, so a captured CUDA graph gets fresh masks on every replay);
+    ``seed`` is the snapshot of it that the kernels of the current forward -- and of its backward, through the
+    autograd contexts, which hold the tensor -- read.  Salts are handed out in call order and restart with every
+    outermost forward (``begin_forward``), so a replayed graph sees the same sequence."""
+
+    GOLD = 0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF
 
     def __init__(self):
+        self.base = None
         self.seed = None
         self.salt = 0
+        self.depth = 0
+
+    def _init(self, s, device):
+        self.base = torch.tensor([int(s) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=device)
+        self.seed = self.base.clone()
 
     def seed_tensor(self, device):
         if self.seed is None or self.seed.device != device:
-            self.seed = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64,
-                                     device=device)
+            s = torch.initial_seed()
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                s += 0x632BE59BD9B4E019 * torch.distributed.get_rank()      # different masks on every replica
+            self._init(s, device)
         return self.seed
 
     def manual_seed(self, s, device):
-        self.seed = torch.tensor([int(s) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=device)
+        self._init(s, device)
 
     def next_salt(self):
         self.salt += 1
@@ -78,17 +89,48 @@ class DropoutState:
         self.salt = 0
 
     def advance(self):
-        if self.seed is not None:
-            self.seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+        """New masks from here on: bump the persistent seed in place, snapshot it for the coming forward."""
+        if self.base is not None:
+            self.base.add_(self.GOLD)
+            self.seed = self.base.clone()
+
+    # -- called by the model containers around their forward ------------------------------------------------
+    def begin_forward(self, training, device):
+        """Outermost forward of a model (or of model.seq2seq / model.postnet called on their own, reference
+        train.py:691-700): restart the salts and, in training, draw a new step seed."""
+        self.depth += 1
+        if self.depth == 1:
+            self.salt = 0
+            if training and device.type == "cuda":
+                self.seed_tensor(device)
+                self.advance()
+
+    def end_forward(self):
+        self.depth -= 1
 
 
 rng = DropoutState()
 
 
+def forward_scope(fn):
+    """Decorator for the ``forward`` of a module the reference's train.py may call on its own (model.postnet,
+    train.py:700): draws the dropout seed / restarts the salts when it is the outermost forward."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, x, *a, **kw):
+        rng.begin_forward(self.training, x.device)
+        try:
+            return fn(self, x, *a, **kw)
+        finally:
+            rng.end_forward()
+    return wrapped
+
+
 def _drop_args(p, training, device):
-    """-> (p_eff, seed_ptr, salt) ; consumes a salt only when dropout is live."""
+    """-> (p_eff, seed tensor | None, salt) ; consumes a salt only when dropout is live."""
     if training and p > 0.0:
-        return float(p), _p(rng.seed_tensor(device)), rng.next_salt()
+        return float(p), rng.seed_tensor(device), rng.next_salt()
     return 0.0, None, 0
 
 
@@ -168,7 +210,8 @@ class _ConvBlockFn(torch.autograd.Function):
         B, C, T = x.shape
         assert v.shape == (2 * C, C, k), "ConvBlock needs in_channels == out_channels"
         w_f, w_b, inv = _wn_conv_fwd(v, g)
-        p, seed_ptr, salt = _drop_args(p_drop, training, x.device)
+        p, seed_t, salt = _drop_args(p_drop, training, x.device)
+        seed_ptr = _p(seed_t)
         need_bwd = any(ctx.needs_input_grad)
         y = torch.empty_like(x)
         a = torch.empty_like(x) if need_bwd else None
@@ -178,13 +221,14 @@ class _ConvBlockFn(torch.autograd.Function):
         if need_bwd:
             ctx.save_for_backward(x, v, g, a, s, w_b, inv)
             ctx.cfg = (k, dilation, causal, mode, residual, p, salt, spk is not None, x.device)
+            ctx.seed_t = seed_t
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, v, g, a, s, w_b, inv = ctx.saved_tensors
         k, dilation, causal, mode, residual, p, salt, has_spk, dev = ctx.cfg
-        seed_ptr = _p(rng.seed_tensor(dev)) if p > 0 else None
+        seed_ptr = _p(ctx.seed_t)          # the forward's own seed snapshot
         dy = _c(dy)
         B, C, T = x.shape
         dab = torch.empty(B, 2 * C, T, device=dev, dtype=torch.float32)
@@ -276,7 +320,8 @@ class _ConvBlockTCFn(torch.autograd.Function):
             scale = torch.empty_like(inv)
             wfwd = torch.empty(npl, k, 2 * C, C, device=dev, dtype=bf)
             wbwd = torch.empty(2, k, C, 2 * C, device=dev, dtype=bf)
-        p, seed_ptr, salt = _drop_args(p_drop, training, dev)
+        p, seed_t, salt = _drop_args(p_drop, training, dev)
+        seed_ptr = _p(seed_t)
         x_btc = torch.empty(npl, B, T, C, device=dev, dtype=bf)
         x_bct = torch.empty(2, k, B, C, T, device=dev, dtype=bf) if (need_bwd and not wgrad_mn) else None
         y = torch.empty_like(x)
@@ -300,6 +345,7 @@ class _ConvBlockTCFn(torch.autograd.Function):
         if need_bwd:
             ctx.save_for_backward(x, v, g, a, s, x_bct, wbwd, inv)
             ctx.cfg = (k, dilation, causal, mode, residual, p, salt, spk is not None, dev)
+            ctx.seed_t = seed_t
             ctx.bias_param = bias if bias.is_leaf else None
             ctx.bank = bank
         return y
@@ -308,7 +354,7 @@ class _ConvBlockTCFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, v, g, a, s, x_bct, wbwd, inv = ctx.saved_tensors
         k, dilation, causal, mode, residual, p, salt, has_spk, dev = ctx.cfg
-        seed_ptr = _p(rng.seed_tensor(dev)) if p > 0 else None
+        seed_ptr = _p(ctx.seed_t)          # the forward's own seed snapshot
         dy = _c(dy)
         B, C, T = x.shape
         bf = torch.bfloat16
@@ -829,7 +875,8 @@ class _AttentionCoreFn(torch.autograd.Function):
         scores = torch.empty(B, Td, Ts, device=dev, dtype=torch.float32)
         # S[t,s] = sum_e q[e,t] k[e,s]                       (reference deepvoice3.py:143, no 1/sqrt(d))
         _bgemm(q, (E * Td, 1, Td), k, (E * Ts, Ts, 1), scores, Td * Ts, Ts, B, Td, Ts, E)
-        p, seed_ptr, salt = _drop_args(p_drop, training, dev)
+        p, seed_t, salt = _drop_args(p_drop, training, dev)
+        seed_ptr = _p(seed_t)
         probs = torch.empty_like(scores)
         pd = torch.empty_like(scores) if p > 0 else None
         lib.call("dv3_softmax_fwd", _p(scores), _p(mask), _p(probs), _p(pd), B * Td, Ts, Td, p, seed_ptr, salt,
@@ -841,6 +888,7 @@ class _AttentionCoreFn(torch.autograd.Function):
         _bgemm(v, (E * Ts, Ts, 1), pv, (Td * Ts, 1, Ts), out, E * Td, Td, B, E, Td, Ts, alpha=scale)
         ctx.save_for_backward(q, k, v, probs, pd)
         ctx.cfg = (p, salt, scale)
+        ctx.seed_t = seed_t
         ctx.mark_non_differentiable()
         return out, probs
 
@@ -852,7 +900,7 @@ class _AttentionCoreFn(torch.autograd.Function):
         Ts = k.shape[2]
         dev = q.device
         dout = _c(dout)
-        seed_ptr = _p(rng.seed_tensor(dev)) if p > 0 else None
+        seed_ptr = _p(ctx.seed_t)          # the forward's own seed snapshot
         pv = pd if pd is not None else probs
         # dPd[t,s] = scale * sum_e dO[e,t] v[e,s]
         dpd = torch.empty(B, Td, Ts, device=dev, dtype=torch.float32)
@@ -871,8 +919,47 @@ class _AttentionCoreFn(torch.autograd.Function):
         return dq, dk, dv, None, None, None
 
 
+class _AttentionTCFn(torch.autograd.Function):
+    """The same contract on the fused tcgen05 kernels (csrc/tc_attn.cu): one launch forward, two backward."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, p_drop, training):
+        _chk(q, k, v)
+        B, E, Td = q.shape
+        Ts = k.shape[2]
+        dev = q.device
+        p, seed_t, salt = _drop_args(p_drop, training, dev)
+        scale = Ts * (1.0 / Ts) ** 0.5                         # deepvoice3.py:170-171
+        probs = torch.empty(B, Td, Ts, device=dev, dtype=torch.float32)
+        out = torch.empty(B, E, Td, device=dev, dtype=torch.float32)
+        lib.call("dv3_tc_attn_fwd", _p(q), _p(k), _p(v), _p(mask), _p(probs), _p(out), B, E, Td, Ts, scale, p,
+                 _p(seed_t), salt, _stream())
+        ctx.save_for_backward(q, k, v, probs)
+        ctx.cfg = (p, salt, scale)
+        ctx.seed_t = seed_t
+        return out, probs
+
+    @staticmethod
+    def backward(ctx, dout, dprobs_ext):
+        q, k, v, probs = ctx.saved_tensors
+        p, salt, scale = ctx.cfg
+        B, E, Td = q.shape
+        Ts = k.shape[2]
+        dev = q.device
+        dout = _c(dout)
+        dpe = _c(dprobs_ext) if dprobs_ext is not None else None
+        ds = torch.empty(B, Td, Ts, device=dev, dtype=torch.float32)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        lib.call("dv3_tc_attn_bwd", _p(dout), _p(q), _p(k), _p(v), _p(probs), _p(dpe), _p(ds), _p(dq), _p(dk), _p(dv),
+                 B, E, Td, Ts, scale, p, _p(ctx.seed_t), salt, _stream())
+        return dq, dk, dv, None, None, None
+
+
 def attention_core(q, k, v, mask=None, p_drop=0.0, training=False):
     """mask: (B, Ts) uint8/bool, 1 = padding.  Returns (out (B,E,Td), probs (B,Td,Ts))."""
     if mask is not None:
         mask = mask.to(torch.uint8).contiguous()
-    return _AttentionCoreFn.apply(_c(q), _c(k), _c(v), mask, float(p_drop), bool(training))
+    B, E, Td = q.shape
+    tc = conv_math in ("tc", "bf16x3") and q.is_cuda and lib.raw("dv3_tc_attn_supported")(B, E, Td, k.shape[2])
+    fn = _AttentionTCFn if tc else _AttentionCoreFn
+    return fn.apply(_c(q), _c(k), _c(v), mask, float(p_drop), bool(training))

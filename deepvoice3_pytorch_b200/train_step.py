@@ -53,13 +53,21 @@ def guided_attention_mask(input_lengths, target_lengths, max_target_len, max_inp
     return W.float()
 
 
-def spec_loss(y_hat, y, mask, masked_loss_weight, binary_divergence_weight, eps=1e-8):
-    """reference train.py:547-582 with priority_freq_weight = 0 (the presets' value)."""
+def spec_loss(y_hat, y, mask, masked_loss_weight, binary_divergence_weight, eps=1e-8, priority_bin=None,
+              priority_w=0.0):
+    """reference train.py:547-582 (torch ops; TrainStep(fused_loss=False) -- the default is csrc/loss.cu)."""
     w = masked_loss_weight
-    l1 = (y_hat - y).abs().mean()
-    if w > 0:
-        mask_ = mask.expand_as(y_hat)
-        l1 = w * ((y_hat * mask_ - y * mask_).abs().sum() / mask_.sum()) + (1 - w) * l1
+
+    def l1_of(a, b):
+        l1 = (a - b).abs().mean()
+        if w > 0:
+            mask_ = mask.expand_as(a)
+            l1 = w * ((a * mask_ - b * mask_).abs().sum() / mask_.sum()) + (1 - w) * l1
+        return l1
+
+    l1 = l1_of(y_hat, y)
+    if priority_bin is not None and priority_w > 0:
+        l1 = (1 - priority_w) * l1 + priority_w * l1_of(y_hat[:, :, :priority_bin], y[:, :, :priority_bin])
     if binary_divergence_weight <= 0:
         return l1, y_hat.new_zeros(())
     logits = torch.log(y_hat + eps) - torch.log(1 - y_hat + eps)
@@ -72,8 +80,14 @@ def spec_loss(y_hat, y, mask, masked_loss_weight, binary_divergence_weight, eps=
     return l1, bd
 
 
+def priority_bin_of(priority_freq, sample_rate, linear_dim):
+    """reference train.py:722."""
+    return int(priority_freq / (sample_rate * 0.5) * linear_dim)
+
+
 def training_loss(outs, batch, r=1, downsample_step=4, masked_loss_weight=0.5, binary_divergence_weight=0.1,
-                  guided_attention_sigma=0.2, use_guided_attention=True):
+                  guided_attention_sigma=0.2, use_guided_attention=True, priority_freq=3000, priority_freq_weight=0.0,
+                  sample_rate=22050):
     """Total loss of one step with seq2seq and postnet trained jointly (reference train.py:665-740)."""
     mel_out, lin_out, attn, done_hat = outs
     mel, y, done = batch["mel"], batch["y"], batch["done"]
@@ -87,7 +101,9 @@ def training_loss(outs, batch, r=1, downsample_step=4, masked_loss_weight=0.5, b
     l1, bd = spec_loss(mel_out[:, :-r, :], mel[:, r:, :], dec_mask, masked_loss_weight, w)
     loss = (1 - w) * l1 + w * bd
     loss = loss + F.binary_cross_entropy(done_hat, done)
-    l1, bd = spec_loss(lin_out[:, :-r, :], y[:, r:, :], tgt_mask, masked_loss_weight, w)
+    l1, bd = spec_loss(lin_out[:, :-r, :], y[:, r:, :], tgt_mask, masked_loss_weight, w,
+                       priority_bin=priority_bin_of(priority_freq, sample_rate, lin_out.size(-1)),
+                       priority_w=priority_freq_weight)
     loss = loss + (1 - w) * l1 + w * bd
     if use_guided_attention:
         soft = guided_attention_mask(batch["input_lengths_dev"], tl // r // downsample_step, attn.size(-2),
@@ -101,7 +117,7 @@ class _FusedLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mel_out, lin_out, attn, done_hat, mel, y, done, target_lengths, input_lengths, r,
-                downsample_step, w, bw, sigma, use_attn):
+                downsample_step, w, bw, sigma, use_attn, pbin, pw):
         dev = mel_out.device
         vp = lambda t: ctypes.c_void_p(t.data_ptr())
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -112,11 +128,11 @@ class _FusedLossFn(torch.autograd.Function):
         dec_len = (target_lengths // (r * downsample_step)).contiguous()
         B, Td, Dm = mel_out.shape
         lib.call("dv3_spec_loss", vp(mel_out), vp(mel.contiguous()), vp(dec_len), vp(g_mel), vp(loss), B, Td, Dm, r,
-                 float(w), float(bw), st)
+                 float(w), float(bw), 0, 0.0, st)
         _, Tl, Dl = lin_out.shape
         lin_len = target_lengths.contiguous() if downsample_step > 1 else dec_len
         lib.call("dv3_spec_loss", vp(lin_out), vp(y.contiguous()), vp(lin_len), vp(g_lin), vp(loss), B, Tl, Dl, r,
-                 float(w), float(bw), st)
+                 float(w), float(bw), int(pbin), float(pw), st)
         A, _, _, Ts = attn.shape
         dec_len_attn = (target_lengths // r // downsample_step).contiguous()
         lib.call("dv3_aux_loss", vp(done_hat), vp(done.contiguous()), vp(g_done), done_hat.numel(), vp(attn),
@@ -128,17 +144,19 @@ class _FusedLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         g_mel, g_lin, g_attn, g_done = ctx.saved_tensors
-        return (g_mel * gout, g_lin * gout, g_attn * gout, g_done * gout) + (None,) * 11
+        return (g_mel * gout, g_lin * gout, g_attn * gout, g_done * gout) + (None,) * 13
 
 
 def fused_training_loss(outs, batch, r=1, downsample_step=4, masked_loss_weight=0.5, binary_divergence_weight=0.1,
-                        guided_attention_sigma=0.2, use_guided_attention=True):
+                        guided_attention_sigma=0.2, use_guided_attention=True, priority_freq=3000,
+                        priority_freq_weight=0.0, sample_rate=22050):
     """Same value and gradients as ``training_loss`` (reference train.py:665-740), computed by csrc/loss.cu."""
     mel_out, lin_out, attn, done_hat = outs
     return _FusedLossFn.apply(mel_out, lin_out, attn, done_hat, batch["mel"], batch["y"], batch["done"],
                               batch["target_lengths"], batch["input_lengths_dev"], r, downsample_step,
                               masked_loss_weight, binary_divergence_weight, guided_attention_sigma,
-                              use_guided_attention)
+                              use_guided_attention, priority_bin_of(priority_freq, sample_rate, lin_out.size(-1)),
+                              priority_freq_weight)
 
 
 class ParameterArena:
@@ -167,6 +185,19 @@ class ParameterArena:
     def zero_grad(self):
         self.grad.zero_()
 
+    def broadcast(self, model=None, src=0):
+        """Replica consistency at start-up (what DistributedDataParallel does at construction): every rank takes
+        rank ``src``'s parameter arena, plus -- when ``model`` is given -- the parameters outside the arena (frozen
+        position tables / embeddings) and the buffers."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        dist.broadcast(self.flat, src)
+        if model is not None:
+            inside = {id(p) for p in self.params}
+            for t in list(model.parameters()) + list(model.buffers()):
+                if id(t) not in inside:
+                    dist.broadcast(t.data, src)
+
     def all_reduce_grads(self):
         """The one exchange step of the data-parallel path: sum the flat gradient arena over all ranks (NCCL over
         NVLink on GPUs; gloo in the CPU tests).  The 1/world average is applied by the optimizer (hyper[3])."""
@@ -186,9 +217,10 @@ class FlatAdam:
         self.hyper = torch.zeros(4, device=dev)
         # ring of pinned staging slots: the host may run several steps ahead of the stream, so a slot is only
         # rewritten after the copy that last read it has completed (event wait, normally already signalled)
-        self._slots = [torch.zeros(4).pin_memory() for _ in range(4)]
+        self._slots = [torch.zeros(4).pin_memory() if dev.type == "cuda" else torch.zeros(4) for _ in range(4)]
         self._events = [None] * 4
         self.sumsq = torch.zeros(1, device=dev)
+        self._scratch = torch.zeros(lib.raw("dv3_sumsq_scratch_floats")(), device=dev) if dev.type == "cuda" else None
         self.t = 0
 
     def set_hyper(self, lr, grad_scale=1.0):
@@ -208,8 +240,8 @@ class FlatAdam:
         """Device-only part (graph-capturable): grad norm -> clip -> Adam."""
         a = self.arena
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        self.sumsq.zero_()
-        lib.call("dv3_sumsq", ctypes.c_void_p(a.grad.data_ptr()), a.numel, ctypes.c_void_p(self.sumsq.data_ptr()), st)
+        lib.call("dv3_sumsq", ctypes.c_void_p(a.grad.data_ptr()), a.numel, ctypes.c_void_p(self.sumsq.data_ptr()),
+                 ctypes.c_void_p(self._scratch.data_ptr()), st)
         lib.call("dv3_adam_clip", ctypes.c_void_p(a.flat.data_ptr()), ctypes.c_void_p(a.grad.data_ptr()),
                  ctypes.c_void_p(self.m.data_ptr()), ctypes.c_void_p(self.v.data_ptr()), a.numel,
                  ctypes.c_void_p(self.hyper.data_ptr()), ctypes.c_void_p(self.sumsq.data_ptr()),
@@ -218,14 +250,59 @@ class FlatAdam:
     def grad_norm(self):
         return self.sumsq.sqrt() * self.hyper[3]
 
+    # -- checkpoint format of torch.optim.Adam (what reference train.py:save_checkpoint stores under "optimizer",
+    #    train.py:787-810, and load_checkpoint restores, :843-860): parameter i of get_trainable_parameters() <->
+    #    state[i] = {step, exp_avg, exp_avg_sq}
+    def state_dict(self):
+        a = self.arena
+        state = {}
+        for i, (p, o) in enumerate(zip(a.params, a.offsets)):
+            n = p.numel()
+            state[i] = {"step": torch.tensor(float(self.t)),
+                        "exp_avg": self.m[o:o + n].view_as(p).clone(),
+                        "exp_avg_sq": self.v[o:o + n].view_as(p).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(a.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        """Accepts a torch.optim.Adam state_dict over the same parameter list (e.g. from a reference checkpoint)."""
+        a = self.arena
+        groups = sd["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) != len(a.params):
+            raise ValueError("optimizer state has %d parameters, the model %d" % (len(ids), len(a.params)))
+        g0 = groups[0]
+        if g0.get("weight_decay", 0) != 0 or g0.get("amsgrad", False):
+            raise ValueError("FlatAdam implements plain Adam: weight_decay / amsgrad states cannot be loaded")
+        self.lr, self.betas, self.eps = g0["lr"], tuple(g0["betas"]), g0["eps"]
+        steps = set()
+        self.m.zero_()
+        self.v.zero_()
+        for i, p, o in zip(ids, a.params, a.offsets):
+            st = sd["state"].get(i)
+            if st is None:                      # parameter that never received a gradient
+                continue
+            n = p.numel()
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError("optimizer state %d has shape %s, parameter %s" % (i, tuple(st["exp_avg"].shape),
+                                                                                   tuple(p.shape)))
+            self.m[o:o + n].view_as(p).copy_(st["exp_avg"])
+            self.v[o:o + n].view_as(p).copy_(st["exp_avg_sq"])
+            steps.add(int(st["step"]))
+        if len(steps) > 1:
+            raise ValueError("per-parameter step counts differ (%s): not representable in a flat Adam" % sorted(steps))
+        self.t = steps.pop() if steps else 0
+
 
 class TrainStep:
     """model + losses + flat optimizer (+ NCCL gradient all-reduce when torch.distributed is initialised)."""
 
     def __init__(self, model, init_lr=5e-4, betas=(0.5, 0.9), eps=1e-6, clip_thresh=0.1, r=1, downsample_step=4,
                  masked_loss_weight=0.5, binary_divergence_weight=0.1, guided_attention_sigma=0.2,
-                 use_guided_attention=True, lr_schedule=noam_learning_rate_decay, use_graph=False,
-                 fused_loss=True, weight_bank=None):
+                 use_guided_attention=True, priority_freq=3000, priority_freq_weight=0.0, sample_rate=22050,
+                 lr_schedule=noam_learning_rate_decay, use_graph=False, fused_loss=True, weight_bank=None):
         self.model = model
         self.arena = ParameterArena(model)
         self.opt = FlatAdam(self.arena, init_lr, betas, eps, clip_thresh)
@@ -233,7 +310,8 @@ class TrainStep:
         self.loss_kw = dict(r=r, downsample_step=downsample_step, masked_loss_weight=masked_loss_weight,
                             binary_divergence_weight=binary_divergence_weight,
                             guided_attention_sigma=guided_attention_sigma,
-                            use_guided_attention=use_guided_attention)
+                            use_guided_attention=use_guided_attention, priority_freq=priority_freq,
+                            priority_freq_weight=priority_freq_weight, sample_rate=sample_rate)
         self.loss_fn = fused_training_loss if fused_loss else training_loss
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.global_step = 0
@@ -245,6 +323,21 @@ class TrainStep:
         if weight_bank is None:
             weight_bank = os.environ.get("DV3_WEIGHT_BANK", "1") == "1"
         self.bank = WeightBank() if weight_bank else None
+        self.arena.broadcast(model)             # replicas start from rank 0's weights (no-op for world == 1)
+
+    # -- checkpointing: the reference's checkpoint keys (train.py:787-810) ---------------------------------
+    def state_dict(self, global_epoch=0):
+        return {"state_dict": self.model.state_dict(), "optimizer": self.opt.state_dict(),
+                "global_step": self.global_step, "global_epoch": global_epoch}
+
+    def load_state_dict(self, ckpt, load_optimizer=True):
+        """Resume from ``state_dict()`` or from a reference checkpoint (same keys).  Restores the Adam moments, the
+        bias-correction step and the position in the learning-rate schedule."""
+        self.model.load_state_dict(ckpt["state_dict"])      # copies into the arena views in place
+        if load_optimizer and ckpt.get("optimizer") is not None:
+            self.opt.load_state_dict(ckpt["optimizer"])
+        self.global_step = int(ckpt.get("global_step", 0))
+        return int(ckpt.get("global_epoch", 0))
 
     # -- pieces -------------------------------------------------------------------------------
     def _forward_backward(self, batch):
@@ -273,8 +366,7 @@ class TrainStep:
 
     def _exchange_and_update(self):
         self.arena.all_reduce_grads()                   # sum; the 1/world average is folded into hyper[3]
-        self.opt.apply()
-        ops.rng.advance()                               # fresh dropout masks next step (device-side add)
+        self.opt.apply()          # (fresh dropout masks per step: the model's forward draws a new seed itself)
 
     # -- public -------------------------------------------------------------------------------
     def step(self, batch):
@@ -299,8 +391,12 @@ class TrainStep:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
+                dev = self.arena.flat.device
+                ops.rng.seed_tensor(dev)
+                seed0 = ops.rng.base.clone()
                 for _ in range(2):
                     self._forward_backward(self._static)
+                ops.rng.base.copy_(seed0)           # the warm-up passes do not consume dropout seeds
             torch.cuda.current_stream().wait_stream(s)
             self._graph = torch.cuda.CUDAGraph()
             n0 = lib.raw("dv3_launch_count")()

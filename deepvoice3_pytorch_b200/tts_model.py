@@ -20,10 +20,16 @@ class AttentionSeq2Seq(nn.Module):
 
     def forward(self, text_sequences, mel_targets=None, speaker_embed=None, text_positions=None,
                 frame_positions=None, input_lengths=None):
-        memory = self.encoder(text_sequences, lengths=input_lengths, speaker_embed=speaker_embed)
-        # -> mel (B, T//r, mel_dim*r), alignments (N, B, T_dec, T_text), done (B, T//r, 1), decoder states
-        return self.decoder(memory, mel_targets, text_positions=text_positions, frame_positions=frame_positions,
-                            speaker_embed=speaker_embed, lengths=input_lengths)
+        # reference train.py:691-694 also calls model.seq2seq(...) on its own: a new dropout seed per training
+        # forward is drawn by whichever container is outermost (ops.DropoutState.begin_forward)
+        ops.rng.begin_forward(self.training, text_sequences.device)
+        try:
+            memory = self.encoder(text_sequences, lengths=input_lengths, speaker_embed=speaker_embed)
+            # -> mel (B, T//r, mel_dim*r), alignments (N, B, T_dec, T_text), done (B, T//r, 1), decoder states
+            return self.decoder(memory, mel_targets, text_positions=text_positions,
+                                frame_positions=frame_positions, speaker_embed=speaker_embed, lengths=input_lengths)
+        finally:
+            ops.rng.end_forward()
 
 
 class MultiSpeakerTTSModel(nn.Module):
@@ -76,13 +82,18 @@ class MultiSpeakerTTSModel(nn.Module):
                 frame_positions=None, input_lengths=None):
         """-> mel_outputs (B, T, mel_dim), linear_outputs (B, T*ds, linear_dim), alignments (N, B, T_dec, T_text),
         done (B, T_dec, 1)."""
-        ops.rng.start_forward()                       # dropout call-site salts restart with every forward
-        batch = text_sequences.size(0)
-        spk = self._speaker_embedding(speaker_ids)
-        mel, alignments, done, states = self.seq2seq(text_sequences, mel_targets, spk, text_positions,
-                                                     frame_positions, input_lengths)
-        mel = mel.reshape(batch, -1, self.mel_dim)    # un-group the r frames per decoder step
-        post_in = states.reshape(batch, mel.size(1), -1) if self.use_decoder_state_for_postnet_input else mel
-        linear = self.postnet(post_in, spk)
-        assert linear.size(-1) == self.linear_dim
-        return mel, linear, alignments, done
+        # dropout: call-site salts restart and (in training) a new step seed is drawn with every forward, so
+        # model(...) / loss.backward() / optimizer.step() loops get fresh masks without any TrainStep
+        ops.rng.begin_forward(self.training, text_sequences.device)
+        try:
+            batch = text_sequences.size(0)
+            spk = self._speaker_embedding(speaker_ids)
+            mel, alignments, done, states = self.seq2seq(text_sequences, mel_targets, spk, text_positions,
+                                                         frame_positions, input_lengths)
+            mel = mel.reshape(batch, -1, self.mel_dim)    # un-group the r frames per decoder step
+            post_in = states.reshape(batch, mel.size(1), -1) if self.use_decoder_state_for_postnet_input else mel
+            linear = self.postnet(post_in, spk)
+            assert linear.size(-1) == self.linear_dim
+            return mel, linear, alignments, done
+        finally:
+            ops.rng.end_forward()

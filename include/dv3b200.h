@@ -122,11 +122,28 @@ int dv3_bgemm(const float* A, long long sAb, long long sAm, long long sAk, const
               long long sBk, long long sBn, float* C, long long sCb, int ldc, int batch, int M, int N, int K,
               float alpha, int accumulate, void* stream);
 
+/* ---- fused tensor-core attention (tcgen05, split-bf16 operands staged and split in-kernel): reference
+ * deepvoice3.py:132-176 between the projections.  q (B,E,Td), k / v (B,E,Ts), mask (B,Ts) bytes (1 = padding) or
+ * null -> probs (B,Td,Ts) = softmax(q^T k) (pre-dropout, returned as the alignment), out (B,E,Td) =
+ * scale * v . dropout(probs)^T.  Backward: dout (B,E,Td), dprobs (B,Td,Ts) gradient arriving at the returned
+ * probabilities (or null) -> dq, dk, dv; ds is a (B,Td,Ts) scratch.  Shapes: dv3_tc_attn_supported (Ts <= 128,
+ * E % 16 == 0, E <= 256); others go through dv3_bgemm + dv3_softmax_*. */
+int dv3_tc_attn_supported(int B, int E, int Td, int Ts);
+int dv3_tc_attn_fwd(const float* q, const float* k, const float* v, const unsigned char* mask, float* probs,
+                    float* out, int B, int E, int Td, int Ts, float scale, float p_drop,
+                    const unsigned long long* seed_ptr, unsigned salt, void* stream);
+int dv3_tc_attn_bwd(const float* dout, const float* q, const float* k, const float* v, const float* probs,
+                    const float* dprobs, float* ds, float* dq, float* dk, float* dv, int B, int E, int Td, int Ts,
+                    float scale, float p_drop, const unsigned long long* seed_ptr, unsigned salt, void* stream);
+
 /* ---- optimizer step over a flat fp32 arena: reference train.py:756-759 (clip_grad_norm_ + Adam.step).
- * dv3_sumsq: out[0] += sum(x^2) (zero it first).  dv3_adam_clip: g' = g*hyper[3]*min(1, max_norm/(||g*hyper[3]||+1e-6))
+ * dv3_sumsq: out[0] = sum(x^2), deterministic (per-block partials in `scratch`, summed in index order by the block
+ * that finishes last: bit-identical on every data-parallel replica); scratch = dv3_sumsq_scratch_floats() floats,
+ * zero-filled once by the caller.  dv3_adam_clip: g' = g*hyper[3]*min(1, max_norm/(||g*hyper[3]||+1e-6))
  * (max_norm <= 0: no clipping), then torch.optim.Adam's update with lr=hyper[0], bias corrections hyper[1], hyper[2].
  * hyper (4 floats) and sumsq live in device memory: no host sync, graph-replayable. */
-int dv3_sumsq(const float* x, long long n, float* out, void* stream);
+int dv3_sumsq_scratch_floats(void);
+int dv3_sumsq(const float* x, long long n, float* out, float* scratch, void* stream);
 int dv3_adam_clip(float* p, const float* g, float* m, float* v, long long n, const float* hyper,
                   const float* sumsq, float beta1, float beta2, float eps, float max_norm, void* stream);
 
@@ -208,10 +225,12 @@ int dv3_tc_wgrad(const void* dy, const void* xs, float* dw_partials, long long s
 /* ---- fused training losses + gradients: reference train.py:537-601 (spec_loss, guided_attention) and :704-740.
  * dv3_spec_loss: pairs (y_hat[b,t], y[b,t+r]), t < T-r; lengths int64 [B] valid target frames; adds
  * (1-bw)*L1 + bw*binary_divergence (each = w*masked_mean + (1-w)*mean) to loss[0]; grad (B,T,D) = dLoss/dy_hat.
+ * priority_bin > 0 and priority_weight > 0: L1 = (1-pw)*L1(all D bins) + pw*L1(bins < priority_bin), train.py:559-567.
  * dv3_aux_loss: adds BCE(done_hat, done) and, if use_attn, mean(attn*W) with the guided-attention mask
  * W[b,t,n] = 1-exp(-(n/in_len[b] - t/dec_len[b])^2/(2 sigma^2)) built on the fly; writes both gradients. */
 int dv3_spec_loss(const float* y_hat, const float* y, const long long* lengths, float* grad, float* loss, int B,
-                  int T, int D, int r, float masked_loss_weight, float binary_divergence_weight, void* stream);
+                  int T, int D, int r, float masked_loss_weight, float binary_divergence_weight, int priority_bin,
+                  float priority_weight, void* stream);
 int dv3_aux_loss(const float* done_hat, const float* done, float* d_done, long long n_done, const float* attn,
                  float* d_attn, const long long* in_len, const long long* dec_len, int A, int B, int Td, int Ts,
                  float sigma, int use_attn, float* loss, void* stream);

@@ -299,14 +299,21 @@ def sequence_mask(lengths, max_len):
     return (torch.arange(max_len)[None, :] < lengths[:, None]).to(torch.float32)
 
 
-def spec_loss(y_hat, y, mask, masked_loss_weight=0.5, binary_divergence_weight=0.1, eps=1e-8):
-    """reference train.py:547-582 with priority_freq_weight=0 (the presets' value)."""
+def spec_loss(y_hat, y, mask, masked_loss_weight=0.5, binary_divergence_weight=0.1, eps=1e-8, priority_bin=None,
+              priority_w=0.0):
+    """reference train.py:547-582 (pinned: tests/golden/train_fns.npz ``specloss*``)."""
     w = masked_loss_weight
-    l1 = (y_hat - y).abs().mean()
-    if w > 0:
-        mask_ = mask.expand_as(y_hat)
-        masked_l1 = ((y_hat * mask_) - (y * mask_)).abs().sum() / mask_.sum()
-        l1 = w * masked_l1 + (1 - w) * l1
+
+    def l1_of(a, b):
+        l1 = (a - b).abs().mean()
+        if w > 0:
+            mask_ = mask.expand_as(a)
+            l1 = w * (((a * mask_) - (b * mask_)).abs().sum() / mask_.sum()) + (1 - w) * l1
+        return l1
+
+    l1 = l1_of(y_hat, y)
+    if priority_bin is not None and priority_w > 0:          # train.py:559-567
+        l1 = (1 - priority_w) * l1 + priority_w * l1_of(y_hat[:, :, :priority_bin], y[:, :, :priority_bin])
     if binary_divergence_weight <= 0:
         return l1, y.new_zeros(1)
     logits = torch.log(y_hat + eps) - torch.log(1 - y_hat + eps)
@@ -332,21 +339,29 @@ def guided_attentions(input_lengths, target_lengths, max_target_len, max_input_l
 
 
 def training_loss(outs, mel, y, done, input_lengths, target_lengths, r=1, downsample_step=4,
-                  masked_loss_weight=0.5, binary_divergence_weight=0.1, guided_sigma=0.2):
-    """reference train.py:665-740: total loss of one step (both seq2seq and postnet trained)."""
+                  masked_loss_weight=0.5, binary_divergence_weight=0.1, guided_sigma=0.2, use_guided_attention=True,
+                  priority_freq=3000, priority_freq_weight=0.0, sample_rate=22050):
+    """reference train.py:665-740: total loss of one step (both seq2seq and postnet trained).  Pinned by the ``step*``
+    cases of tests/golden/train_fns.npz, which come from running the reference's train() itself."""
     mel_out, lin_out, attn, done_hat = outs
     tl = torch.as_tensor(np.asarray(target_lengths))
-    dec_mask = sequence_mask(tl // (r * downsample_step), mel.size(1)).unsqueeze(-1)
-    tgt_mask = sequence_mask(tl, y.size(1)).unsqueeze(-1) if downsample_step > 1 else dec_mask
-    dec_mask, tgt_mask = dec_mask[:, r:, :], tgt_mask[:, r:, :]
+    dec_mask = tgt_mask = None
+    if masked_loss_weight > 0:
+        dec_mask = sequence_mask(tl // (r * downsample_step), mel.size(1)).unsqueeze(-1)
+        tgt_mask = sequence_mask(tl, y.size(1)).unsqueeze(-1) if downsample_step > 1 else dec_mask
+        dec_mask, tgt_mask = dec_mask[:, r:, :], tgt_mask[:, r:, :]
     w = binary_divergence_weight
     l1, bd = spec_loss(mel_out[:, :-r, :], mel[:, r:, :], dec_mask, masked_loss_weight, w)
     mel_loss = (1 - w) * l1 + w * bd
     done_loss = F.binary_cross_entropy(done_hat, done)
-    l1, bd = spec_loss(lin_out[:, :-r, :], y[:, r:, :], tgt_mask, masked_loss_weight, w)
+    pbin = int(priority_freq / (sample_rate * 0.5) * lin_out.size(-1))          # train.py:722
+    l1, bd = spec_loss(lin_out[:, :-r, :], y[:, r:, :], tgt_mask, masked_loss_weight, w, priority_bin=pbin,
+                       priority_w=priority_freq_weight)
     lin_loss = (1 - w) * l1 + w * bd
-    dec_lengths = np.asarray(target_lengths) // r // downsample_step
-    soft = torch.from_numpy(guided_attentions(np.asarray(input_lengths), dec_lengths,
-                                              attn.size(-2), attn.size(-1), guided_sigma))
-    attn_loss = (attn * soft.to(attn.dtype)).mean()
-    return mel_loss + lin_loss + done_loss + attn_loss
+    loss = mel_loss + lin_loss + done_loss
+    if use_guided_attention:
+        dec_lengths = np.asarray(target_lengths) // r // downsample_step
+        soft = torch.from_numpy(guided_attentions(np.asarray(input_lengths), dec_lengths,
+                                                  attn.size(-2), attn.size(-1), guided_sigma))
+        loss = loss + (attn * soft.to(attn.dtype)).mean()
+    return loss

@@ -29,12 +29,16 @@ def test_flat_adam_matches_reference_math():
     pr, mr, vr = p.clone(), m.clone(), v.clone()
     hyper = torch.zeros(4, device="cuda")
     sumsq = torch.zeros(1, device="cuda")
+    scratch = torch.zeros(lib.raw("dv3_sumsq_scratch_floats")(), device="cuda")
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     vp = lambda t: ctypes.c_void_p(t.data_ptr())
     for t in range(1, 4):
         hyper.copy_(torch.tensor([1e-3, 1 - 0.5 ** t, 1 - 0.9 ** t, 0.5]))
-        sumsq.zero_()
-        lib.call("dv3_sumsq", vp(g), n, vp(sumsq), st)
+        lib.call("dv3_sumsq", vp(g), n, vp(sumsq), vp(scratch), st)
+        assert float(sumsq) == float(sumsq.clone())
+        again = torch.zeros(1, device="cuda")
+        lib.call("dv3_sumsq", vp(g), n, vp(again), vp(scratch), st)
+        assert float(again) == float(sumsq), "sumsq must be deterministic"
         lib.call("dv3_adam_clip", vp(p), vp(g), vp(m), vp(v), n, vp(hyper), vp(sumsq), 0.5, 0.9, 1e-6, 0.1, st)
         pr, mr, vr = adam_clip_reference(pr, g, mr, vr, t, 1e-3, (0.5, 0.9), 1e-6, 0.1, grad_scale=0.5)
     torch.testing.assert_close(p, pr, rtol=1e-5, atol=1e-6)
@@ -176,3 +180,48 @@ def test_weight_bank_equals_per_layer_weight_norm():
             np.testing.assert_allclose(losses(True, graph), ref, rtol=2e-5)
     finally:
         ops.conv_math = old_math
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["step0", "step1", "step2"])
+def test_fused_loss_kernels_match_reference_train_loop(name):
+    """csrc/loss.cu against the loss of the reference's own train() (tests/golden/train_fns.npz ``step*``: total loss
+    and d(loss)/d(every model output), incl. the priority-bin branch, w = 0 / bw = 0 and guided attention off)."""
+    import golden_util as G
+    from test_train_golden import step_case_inputs
+    from deepvoice3_pytorch_b200.train_step import fused_training_loss
+    case = G.load("train_fns.npz")[name]
+    outs, batch, kw = step_case_inputs(case, "cuda")
+    loss = fused_training_loss(outs, batch, **kw)
+    loss.backward()
+    np.testing.assert_allclose(float(loss), float(case["out"]["loss"]), rtol=1e-5)
+    for o, k in zip(outs, ("mel_out", "lin_out", "attn", "done_hat")):
+        np.testing.assert_allclose(o.grad.cpu().numpy(), case["out"]["grad_" + k], rtol=1e-3, atol=1e-8, err_msg=k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["specloss0", "specloss1", "specloss2", "specloss3", "specloss4"])
+def test_spec_loss_kernel_matches_reference_spec_loss(name):
+    """dv3_spec_loss (r = 0: no frame shift) against the reference's spec_loss on the same tensors."""
+    import ctypes
+    import golden_util as G
+    from deepvoice3_pytorch_b200._lib import lib
+    case = G.load("train_fns.npz")[name]
+    w, bw, pbin, pw = [float(v) for v in case["meta"]["cfg"]]
+    y_hat = torch.from_numpy(case["in"]["y_hat"]).cuda()
+    y = torch.from_numpy(case["in"]["y"]).cuda()
+    lens = torch.from_numpy(case["in"]["lengths"]).cuda()
+    B, T, D = y_hat.shape
+    # the kernel pairs y_hat[:, t] with y[:, t+r] for t < T-r; emulate the un-shifted call by padding one frame
+    r = 1
+    y_hat_p = torch.cat([y_hat, torch.full((B, 1, D), 0.5, device="cuda")], 1).contiguous()
+    y_p = torch.cat([torch.zeros(B, 1, D, device="cuda"), y], 1).contiguous()
+    grad = torch.empty_like(y_hat_p)
+    loss = torch.zeros(1, device="cuda")
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lib.call("dv3_spec_loss", vp(y_hat_p), vp(y_p), vp((lens + r).contiguous()), vp(grad), vp(loss), B, T + 1, D, r,
+             w, bw, max(int(pbin), 0), pw, st)
+    want = (1 - bw) * float(case["out"]["l1"]) + bw * float(case["out"]["bd"])
+    np.testing.assert_allclose(float(loss), want, rtol=1e-5)
+    np.testing.assert_allclose(grad[:, :T].cpu().numpy(), case["out"]["grad"], rtol=1e-3, atol=1e-9)
