@@ -202,11 +202,11 @@ def convblock_roofline(dev, pk, pk_kind):
         xs = torch.empty(2, Bc, T, C, device=dev, dtype=bf)
         ops.lib.call("dv3_tc_split_input", ops._p(x), ops._p(xs), 2, None, Bc, C, T, k, d, 0, 0.0, None, 0,
                      ops._stream())
-        name = "tcgen05 gated ConvBlock forward (persistent tc_conv_persist_kernel<GATED, BK=64>) via dv3_tc_convblock_fwd"
+        name = "tcgen05 gated ConvBlock forward (persistent tc_conv_kernel<GATED, BK=64>) via dv3_tc_convblock_fwd"
 
         def launch():
             ops.lib.call("dv3_tc_convblock_fwd", ops._p(xs), ops._p(wfwd), 2, ops._p(bias), None, ops._p(x), ops._p(y),
-                         ops._p(sa), ops._p(ss), Bc, C, T, k, d, 0, 0, 1, ops._stream())
+                         ops._p(sa), ops._p(ss), Bc, C, T, k, d, 0, 0, 1, None, ops._stream())
         mma_passes = 3
     else:
         w_f, w_b, inv = ops._wn_conv_fwd(v, g)

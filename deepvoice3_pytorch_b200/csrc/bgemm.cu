@@ -85,7 +85,7 @@ static int launch_bgemm(const BgemmParams& p, int batch, cudaStream_t st) {
         configured = true;
     }
     dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, GEMM_BM), batch);
-    gemm_simt_kernel<P, 64><<<grid, GEMM_THREADS, gemm_smem_bytes<64>(), st>>>(p);
+    launch_k(gemm_simt_kernel<P, 64>, grid, GEMM_THREADS, gemm_smem_bytes<64>(), st, p);
     return check_launch("bgemm");
 }
 

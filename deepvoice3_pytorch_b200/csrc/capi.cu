@@ -2,6 +2,7 @@
 // message of the most recent failure on the calling thread is available through dv3_last_error().
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace dv3 {
 static thread_local char g_err[512] = "";
@@ -11,6 +12,23 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+const Config& config() {
+    static const Config c = [] {
+        Config v;
+        const char* e = getenv("DV3_PDL");
+        v.pdl = (e && atoi(e) == 0) ? 0 : 1;
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        v.sms = sms > 0 ? sms : 148;
+        // measured on B200 (tools/trunc_bias.py): the main accumulator (fp16 x fp16 products) loses 0.56 * 2^-25 of its value per MMA
+        e = getenv("DV3_TC_GAMMA");               // override, in units of 2^-25 per MMA
+        v.tc_gamma = (e ? (float)atof(e) : 0.56f) * 2.98023224e-8f;
+        return v;
+    }();
+    return c;
 }
 
 static unsigned long long g_launches = 0;

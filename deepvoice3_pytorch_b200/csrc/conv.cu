@@ -321,6 +321,7 @@ __global__ void gate_bwd_kernel(const float* __restrict__ dy, const float* __res
                                 const float* __restrict__ s, const float* __restrict__ x,
                                 float* __restrict__ dab, float* __restrict__ dbias, int B, int C, int T,
                                 int mode, int residual) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * C) return;
     const int b = warp / C, c = warp - b * C;
@@ -344,6 +345,7 @@ __global__ void gate_bwd_kernel(const float* __restrict__ dy, const float* __res
 __global__ void bias_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                     float* __restrict__ dyr, float* __restrict__ dbias, int B, int C,
                                     int T, int relu) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * C) return;
     const int c = warp % C;
@@ -380,7 +382,7 @@ static int launch_gemm(const typename P::Params& p, dim3 grid, cudaStream_t st, 
                              gemm_smem_bytes<BN>());
         configured = true;
     }
-    gemm_simt_kernel<P, BN><<<grid, GEMM_THREADS, gemm_smem_bytes<BN>(), st>>>(p);
+    launch_k(gemm_simt_kernel<P, BN>, grid, GEMM_THREADS, gemm_smem_bytes<BN>(), st, p);
     return check_launch(what);
 }
 
@@ -481,7 +483,7 @@ int dv3_conv1d_wgrad(const float* dab, const float* x, float* dw_partials, long 
 int dv3_convblock_gate_bwd(const float* dy, const float* a, const float* s, const float* x, float* dab,
                            float* dbias, int B, int C, int T, int mode, int residual, void* stream) {
     const int warps = B * C, threads = 256;
-    gate_bwd_kernel<<<ceil_div(warps * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+    launch_k(gate_bwd_kernel, ceil_div(warps * 32, threads), threads, 0, (cudaStream_t)stream, 
         dy, a, s, x, dab, dbias, B, C, T, mode, residual);
     return check_launch("convblock_gate_bwd");
 }
@@ -489,7 +491,7 @@ int dv3_convblock_gate_bwd(const float* dy, const float* a, const float* s, cons
 int dv3_bias_act_bwd(const float* dy, const float* y, float* dyr, float* dbias, int B, int C, int T,
                      int relu, void* stream) {
     const int warps = B * C, threads = 256;
-    bias_act_bwd_kernel<<<ceil_div(warps * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+    launch_k(bias_act_bwd_kernel, ceil_div(warps * 32, threads), threads, 0, (cudaStream_t)stream, 
         dy, y, dyr, dbias, B, C, T, relu);
     return check_launch("bias_act_bwd");
 }

@@ -8,6 +8,7 @@ namespace dv3 {
 // reference: every x.transpose(1, 2) between the (B,T,C) attention layout and the (B,C,T) conv layout
 // (deepvoice3.py:86,93,318,324,340-345,355,359,592,602; nyanko.py:66,206,214-217,230,234,402).
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     __shared__ float tile[32][33];
     const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
     const float* src = in + (size_t)b * R * C;
@@ -29,6 +30,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 // ids int64 (N) -> out (N, D).  One warp per row; ids are validated (bit-exact indexing).
 __global__ void embedding_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
                                      float* __restrict__ out, int N, int D, int V, int* __restrict__ err) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (n >= N) return;
     const long long id = ids[n];
@@ -40,6 +42,7 @@ __global__ void embedding_fwd_kernel(const long long* __restrict__ ids, const fl
 // dtable[ids[n]] += dy[n] unless ids[n] == padding_idx (padding_idx < 0: none)
 __global__ void embedding_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dy,
                                      float* __restrict__ dtable, int N, int D, int V, long long padding_idx) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (n >= N) return;
     const long long id = ids[n];
@@ -53,6 +56,7 @@ __global__ void embedding_bwd_kernel(const long long* __restrict__ ids, const fl
 __global__ void sinusoid_fwd_kernel(const long long* __restrict__ pos, const float* __restrict__ table,
                                     const float* __restrict__ w, int nw, float* __restrict__ out, int B,
                                     int T, int D, int P, int* __restrict__ err) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (n >= B * T) return;
     const long long ps = pos[n];
@@ -71,6 +75,7 @@ __global__ void sinusoid_bwd_kernel(const long long* __restrict__ pos, const flo
                                     const float* __restrict__ w, int nw, const float* __restrict__ dy,
                                     float* __restrict__ dtable, float* __restrict__ dw, int B, int T, int D,
                                     int P) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (n >= B * T) return;
     const long long ps = pos[n];
@@ -93,6 +98,7 @@ __global__ void sinusoid_bwd_kernel(const long long* __restrict__ pos, const flo
 // deepvoice3.py:75,80,294,321,588,597 ; same call with the same (seed, salt) is its own backward.
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p,
                                const unsigned long long* __restrict__ seed_ptr, unsigned salt) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const DropCfg d = make_drop(p, seed_ptr, salt);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x)
@@ -106,6 +112,7 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ s, const unsigned c
                                    float* __restrict__ probs, float* __restrict__ pd, int rows, int L,
                                    int rows_per_b, float p, const unsigned long long* __restrict__ seed_ptr,
                                    unsigned salt) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= rows) return;
     const DropCfg d = make_drop(p, seed_ptr, salt);
@@ -138,6 +145,7 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ probs, const float*
                                    const float* __restrict__ dprobs_ext, float* __restrict__ ds, int rows,
                                    int L, float p, const unsigned long long* __restrict__ seed_ptr,
                                    unsigned salt) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= rows) return;
     const DropCfg d = make_drop(p, seed_ptr, salt);
@@ -161,6 +169,7 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ probs, const float*
 // in (B, 2*C, T) rows ordered (j, co)  <->  out (B, C, 2T) with out[b,co,2t+j] = in[b, j*C+co, t]
 __global__ void interleave2_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int T,
                                    int inverse) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const long long total = (long long)B * C * 2 * T;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -187,20 +196,20 @@ extern "C" {
 
 int dv3_transpose(const float* in, float* out, int B, int R, int C, void* stream) {
     DV3_REQUIRE(B <= 65535, "transpose: batch %d > 65535", B);
-    transpose_kernel<<<dim3(ceil_div(C, 32), ceil_div(R, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+    launch_k(transpose_kernel, dim3(ceil_div(C, 32), ceil_div(R, 32), B), dim3(32, 8), 0, (cudaStream_t)stream, 
         in, out, R, C);
     return check_launch("transpose");
 }
 
 int dv3_embedding_fwd(const long long* ids, const float* table, float* out, int N, int D, int V, int* err_flag,
                       void* stream) {
-    embedding_fwd_kernel<<<ceil_div(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(ids, table, out, N, D, V,
+    launch_k(embedding_fwd_kernel, ceil_div(N * 32, 256), 256, 0, (cudaStream_t)stream, ids, table, out, N, D, V,
                                                                                  err_flag);
     return check_launch("embedding_fwd");
 }
 int dv3_embedding_bwd(const long long* ids, const float* dy, float* dtable, int N, int D, int V,
                       long long padding_idx, void* stream) {
-    embedding_bwd_kernel<<<ceil_div(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(ids, dy, dtable, N, D, V,
+    launch_k(embedding_bwd_kernel, ceil_div(N * 32, 256), 256, 0, (cudaStream_t)stream, ids, dy, dtable, N, D, V,
                                                                                  padding_idx);
     return check_launch("embedding_bwd");
 }
@@ -208,13 +217,13 @@ int dv3_embedding_bwd(const long long* ids, const float* dy, float* dtable, int 
 int dv3_sinusoid_fwd(const long long* pos, const float* table, const float* w, int nw, float* out, int B, int T,
                      int D, int P, int* err_flag, void* stream) {
     DV3_REQUIRE(nw == 1 || nw == B, "sinusoid_fwd: need 1 or B position rates, got %d", nw);
-    sinusoid_fwd_kernel<<<ceil_div(B * T * 32, 256), 256, 0, (cudaStream_t)stream>>>(pos, table, w, nw, out, B,
+    launch_k(sinusoid_fwd_kernel, ceil_div(B * T * 32, 256), 256, 0, (cudaStream_t)stream, pos, table, w, nw, out, B,
                                                                                     T, D, P, err_flag);
     return check_launch("sinusoid_fwd");
 }
 int dv3_sinusoid_bwd(const long long* pos, const float* table, const float* w, int nw, const float* dy,
                      float* dtable, float* dw, int B, int T, int D, int P, void* stream) {
-    sinusoid_bwd_kernel<<<ceil_div(B * T * 32, 256), 256, 0, (cudaStream_t)stream>>>(pos, table, w, nw, dy,
+    launch_k(sinusoid_bwd_kernel, ceil_div(B * T * 32, 256), 256, 0, (cudaStream_t)stream, pos, table, w, nw, dy,
                                                                                     dtable, dw, B, T, D, P);
     return check_launch("sinusoid_bwd");
 }
@@ -222,25 +231,25 @@ int dv3_sinusoid_bwd(const long long* pos, const float* table, const float* w, i
 int dv3_dropout(const float* x, float* y, long long n, float p, const unsigned long long* seed_ptr, unsigned salt,
                 void* stream) {
     DV3_REQUIRE(n < (1LL << 32), "dropout: tensor too large");
-    dropout_kernel<<<ew_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, seed_ptr, salt);
+    launch_k(dropout_kernel, ew_blocks(n, 256), 256, 0, (cudaStream_t)stream, x, y, n, p, seed_ptr, salt);
     return check_launch("dropout");
 }
 
 int dv3_softmax_fwd(const float* s, const unsigned char* mask, float* probs, float* pd, int rows, int L,
                     int rows_per_b, float p, const unsigned long long* seed_ptr, unsigned salt, void* stream) {
-    softmax_fwd_kernel<<<ceil_div(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(s, mask, probs, pd, rows, L,
+    launch_k(softmax_fwd_kernel, ceil_div(rows * 32, 256), 256, 0, (cudaStream_t)stream, s, mask, probs, pd, rows, L,
                                                                                   rows_per_b, p, seed_ptr, salt);
     return check_launch("softmax_fwd");
 }
 int dv3_softmax_bwd(const float* probs, const float* dpd, const float* dprobs_ext, float* ds, int rows, int L,
                     float p, const unsigned long long* seed_ptr, unsigned salt, void* stream) {
-    softmax_bwd_kernel<<<ceil_div(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(probs, dpd, dprobs_ext, ds,
+    launch_k(softmax_bwd_kernel, ceil_div(rows * 32, 256), 256, 0, (cudaStream_t)stream, probs, dpd, dprobs_ext, ds,
                                                                                   rows, L, p, seed_ptr, salt);
     return check_launch("softmax_bwd");
 }
 
 int dv3_interleave2(const float* in, float* out, int B, int C, int T, int inverse, void* stream) {
-    interleave2_kernel<<<ew_blocks((long long)B * C * 2 * T, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, C,
+    launch_k(interleave2_kernel, ew_blocks((long long)B * C * 2 * T, 256), 256, 0, (cudaStream_t)stream, in, out, B, C,
                                                                                                   T, inverse);
     return check_launch("interleave2");
 }

@@ -82,6 +82,7 @@ __device__ __forceinline__ void tile_mma(const float* __restrict__ As, const flo
 //   struct BLoad (same, n_tile);  static int num_chunks(p,z);  static void epilogue(p,acc,m_tile,n_tile,z,tx,ty)
 template <class P, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_simt_kernel(const __grid_constant__ typename P::Params p) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     extern __shared__ __align__(16) float smem[];
     float* As[2] = {smem, smem + GEMM_BK * GEMM_BM};
     float* Bs[2] = {smem + 2 * GEMM_BK * GEMM_BM, smem + 2 * GEMM_BK * GEMM_BM + GEMM_BK * BN};

@@ -21,6 +21,7 @@ constexpr float kSqrtHalf = 0.70710678118654752f;
 // one warp per output channel c (GLU / highway: rows c and C + c); BT batch rows per pass
 template <int BT>
 __global__ void __launch_bounds__(256) inc_conv_step_kernel(const __grid_constant__ Dv3IncStep p) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int gated = p.mode != 0;
     const int C = gated ? p.Cout / 2 : p.Cout;
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256) inc_conv_step_kernel(const __grid_constan
 
 // one CTA per batch row: scores = q . keys, monotonic window, softmax, context = probs . values * Ts*sqrt(1/Ts)
 __global__ void __launch_bounds__(256) inc_attn_step_kernel(const __grid_constant__ Dv3IncAttn p) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     extern __shared__ float sm[];
     float* q = sm;                 // [E]
     float* sc = sm + p.E;          // [Ts]
@@ -202,7 +204,8 @@ __global__ void __launch_bounds__(256) inc_attn_step_kernel(const __grid_constan
     }
 }
 
-__global__ void inc_advance_kernel(int* t) { *t += 1; }
+__global__ void inc_advance_kernel(int* t) {
+    pdl_trigger(); pdl_wait(); *t += 1; }
 
 }  // namespace dv3
 
@@ -218,9 +221,9 @@ int dv3_inc_conv_step(const Dv3IncStep* p, void* stream) {
     const int C = p->mode != 0 ? p->Cout / 2 : p->Cout;
     const int blocks = (C * 32 + 255) / 256;
     cudaStream_t st = (cudaStream_t)stream;
-    if (p->B == 1) inc_conv_step_kernel<1><<<blocks, 256, 0, st>>>(*p);
-    else if (p->B == 2) inc_conv_step_kernel<2><<<blocks, 256, 0, st>>>(*p);
-    else inc_conv_step_kernel<4><<<blocks, 256, 0, st>>>(*p);
+    if (p->B == 1) launch_k(inc_conv_step_kernel<1>, blocks, 256, 0, st, *p);
+    else if (p->B == 2) launch_k(inc_conv_step_kernel<2>, blocks, 256, 0, st, *p);
+    else launch_k(inc_conv_step_kernel<4>, blocks, 256, 0, st, *p);
     return check_launch("inc_conv_step");
 }
 
@@ -228,12 +231,12 @@ int dv3_inc_attn_step(const Dv3IncAttn* p, void* stream) {
     DV3_REQUIRE(p && p->B > 0 && p->E > 0 && p->Ts > 0, "inc_attn_step: bad shape");
     const size_t smem = (size_t)(p->E + p->Ts) * sizeof(float);
     DV3_REQUIRE(smem <= 48 * 1024, "inc_attn_step: E + Ts = %d floats exceed 48 KB of shared memory", p->E + p->Ts);
-    inc_attn_step_kernel<<<p->B, 256, smem, (cudaStream_t)stream>>>(*p);
+    launch_k(inc_attn_step_kernel, p->B, 256, smem, (cudaStream_t)stream, *p);
     return check_launch("inc_attn_step");
 }
 
 int dv3_inc_advance(int* t_ptr, void* stream) {
-    inc_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(t_ptr);
+    launch_k(inc_advance_kernel, 1, 1, 0, (cudaStream_t)stream, t_ptr);
     return check_launch("inc_advance");
 }
 

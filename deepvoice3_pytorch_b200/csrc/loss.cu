@@ -30,6 +30,7 @@ __global__ void spec_loss_kernel(const float* __restrict__ y_hat, const float* _
                                  const long long* __restrict__ lengths, float* __restrict__ grad,
                                  float* __restrict__ loss, int B, int T, int D, int r, float w, float bw,
                                  float eps, int pbin, float pw) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     __shared__ float red[8];
     __shared__ float s_inv_sm;
     if (threadIdx.x == 0) {
@@ -86,6 +87,7 @@ __global__ void aux_loss_kernel(const float* __restrict__ done_hat, const float*
                                 float* __restrict__ d_attn, const long long* __restrict__ in_len,
                                 const long long* __restrict__ dec_len, int A, int B, int Td, int Ts, float sigma,
                                 int use_attn, float* __restrict__ loss) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     __shared__ float red[8];
     float acc = 0.f;
     const long long stride = (long long)gridDim.x * blockDim.x, start = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -112,6 +114,9 @@ __global__ void aux_loss_kernel(const float* __restrict__ done_hat, const float*
             acc += inv_na * attn[i] * wv;
             d_attn[i] = inv_na * wv;
         }
+    } else if (d_attn) {
+        const long long n_attn = (long long)A * B * Td * Ts;
+        for (long long i = start; i < n_attn; i += stride) d_attn[i] = 0.f;
     }
     const float s = block_sum_256(acc, red);
     if (threadIdx.x == 0) atomicAdd(loss, s);
@@ -131,7 +136,7 @@ int dv3_spec_loss(const float* y_hat, const float* y, const long long* lengths, 
                 "spec_loss: priority_bin=%d (D=%d) priority_weight=%g out of range", priority_bin, D, priority_weight);
     long long blocks = ((long long)B * T * D + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    spec_loss_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(y_hat, y, lengths, grad, loss, B, T, D, r,
+    launch_k(spec_loss_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, y_hat, y, lengths, grad, loss, B, T, D, r,
                                                                    masked_loss_weight, binary_divergence_weight, 1e-8f,
                                                                    priority_bin, priority_weight);
     return check_launch("spec_loss");
@@ -140,7 +145,7 @@ int dv3_spec_loss(const float* y_hat, const float* y, const long long* lengths, 
 int dv3_aux_loss(const float* done_hat, const float* done, float* d_done, long long n_done, const float* attn,
                  float* d_attn, const long long* in_len, const long long* dec_len, int A, int B, int Td, int Ts,
                  float sigma, int use_attn, float* loss, void* stream) {
-    aux_loss_kernel<<<148 * 2, 256, 0, (cudaStream_t)stream>>>(done_hat, done, d_done, n_done, attn, d_attn, in_len,
+    launch_k(aux_loss_kernel, 148 * 2, 256, 0, (cudaStream_t)stream, done_hat, done, d_done, n_done, attn, d_attn, in_len,
                                                               dec_len, A, B, Td, Ts, sigma, use_attn, loss);
     return check_launch("aux_loss");
 }

@@ -16,6 +16,7 @@ constexpr int SUMSQ_MAX_BLOCKS = 148 * 8;
 constexpr int SUMSQ_SCRATCH = 2048;
 __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out,
                              float* __restrict__ scratch) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     float s = 0.f;
     const long long n4 = n >> 2;
     const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -66,6 +67,7 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
                                  float* __restrict__ v, long long n, const float* __restrict__ hyper,
                                  const float* __restrict__ sumsq, float beta1, float beta2, float eps,
                                  float max_norm) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gscale = hyper[3];
     float coef = gscale;
     if (max_norm > 0.f) {
@@ -98,7 +100,7 @@ int dv3_sumsq(const float* x, long long n, float* out, float* scratch, void* str
     long long blocks = (n / 4 + 255) / 256;
     if (blocks > SUMSQ_MAX_BLOCKS) blocks = SUMSQ_MAX_BLOCKS;
     if (blocks < 1) blocks = 1;
-    sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out, scratch);
+    launch_k(sumsq_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, x, n, out, scratch);
     return check_launch("sumsq");
 }
 
@@ -107,7 +109,7 @@ int dv3_adam_clip(float* p, const float* g, float* m, float* v, long long n, con
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    adam_clip_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper, sumsq, beta1, beta2,
+    launch_k(adam_clip_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, n, hyper, sumsq, beta1, beta2,
                                                                    eps, max_norm);
     return check_launch("adam_clip");
 }

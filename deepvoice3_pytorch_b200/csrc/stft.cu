@@ -33,6 +33,7 @@ __device__ __forceinline__ float amp_to_norm_db(float v, float min_level, float 
 }
 
 __global__ void __launch_bounds__(256) stft_mel_kernel(const __grid_constant__ StftParams p) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     __shared__ float zr[NH], zi[NH];
     __shared__ float twr[NH / 2], twi[NH / 2];
     __shared__ float mag[NBINS + 3];
@@ -131,7 +132,7 @@ int dv3_stft_mel(const float* wav, const int* lengths, const float* mel_basis, c
     DV3_REQUIRE(max_frames >= dv3_stft_num_frames(max_len) || max_frames > 0, "stft_mel: bad max_frames");
     StftParams p = {wav, lengths, mel_basis, mel_start, mel_len, linear, mel, max_len, max_frames, n_mels,
                     preemph, min_level_db, ref_level_db};
-    stft_mel_kernel<<<dim3(max_frames, nclips), 256, 0, (cudaStream_t)stream>>>(p);
+    launch_k(stft_mel_kernel, dim3(max_frames, nclips), 256, 0, (cudaStream_t)stream, p);
     return check_launch("stft_mel");
 }
 

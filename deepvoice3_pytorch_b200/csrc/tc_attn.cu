@@ -153,6 +153,7 @@ constexpr int ROWS_SMEM = 65536 + 2 * 65536 + 1024 + 256;
 
 template <int BWD>
 __global__ void __launch_bounds__(AT_THREADS, 1) attn_rows_kernel(const __grid_constant__ AttnParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * 65536);        // [0,1]: stage free, [2]: GEMM1 done, [3]: GEMM2 done
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rows_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
+    pdl_wait();                 // set-up above overlaps the previous kernel's tail; global memory from here on
 
     // ---------------- GEMM 1: D1[t][s] = sum_e A1[e][t0+t] * B1[e][s] -----------------------------------
     const int kchunks = (E + 63) / 64;
@@ -353,6 +355,7 @@ struct AttnColsParams {
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1) attn_cols_kernel(const __grid_constant__ AttnColsParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 131072);            // [0]: chunk MMAs retired
@@ -373,6 +376,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_cols_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
+    pdl_wait();                 // set-up above overlaps the previous kernel's tail; global memory from here on
 
     const int kchunks = (Td + 63) / 64;
     constexpr uint32_t idesc = make_idesc_bf16(128, AT_NS) | (1u << 16);      // A K-major, B MN-major
@@ -474,7 +478,7 @@ int dv3_tc_attn_fwd(const float* q, const float* k, const float* v, const unsign
     AttnParams p = {};
     p.a1 = q; p.b1 = k; p.b2 = v; p.mask = mask; p.probs = probs; p.out = out;
     p.B = B; p.E = E; p.Td = Td; p.Ts = Ts; p.scale = scale; p.p_drop = p_drop; p.seed_ptr = seed_ptr; p.salt = salt;
-    attn_rows_kernel<0><<<dim3((Td + 127) / 128, B), AT_THREADS, ROWS_SMEM, (cudaStream_t)stream>>>(p);
+    launch_k(attn_rows_kernel<0>, dim3((Td + 127) / 128, B), AT_THREADS, ROWS_SMEM, (cudaStream_t)stream, p);
     return check_launch("tc_attn_fwd");
 }
 
@@ -492,12 +496,12 @@ int dv3_tc_attn_bwd(const float* dout, const float* q, const float* k, const flo
     AttnParams p = {};
     p.a1 = dout; p.b1 = v; p.b2 = k; p.probs = const_cast<float*>(probs); p.dprobs = dprobs; p.ds = ds; p.out = dq;
     p.B = B; p.E = E; p.Td = Td; p.Ts = Ts; p.scale = scale; p.p_drop = p_drop; p.seed_ptr = seed_ptr; p.salt = salt;
-    attn_rows_kernel<1><<<dim3((Td + 127) / 128, B), AT_THREADS, ROWS_SMEM, (cudaStream_t)stream>>>(p);
+    launch_k(attn_rows_kernel<1>, dim3((Td + 127) / 128, B), AT_THREADS, ROWS_SMEM, (cudaStream_t)stream, p);
     if (check_launch("tc_attn_bwd(rows)")) return 1;
     AttnColsParams c = {};
     c.dout = dout; c.q = q; c.probs = probs; c.ds = ds; c.dv = dv; c.dk = dk;
     c.B = B; c.E = E; c.Td = Td; c.Ts = Ts; c.scale = scale; c.p_drop = p_drop; c.seed_ptr = seed_ptr; c.salt = salt;
-    attn_cols_kernel<<<dim3((E + 127) / 128, B), AT_THREADS, COLS_SMEM, (cudaStream_t)stream>>>(c);
+    launch_k(attn_cols_kernel, dim3((E + 127) / 128, B), AT_THREADS, COLS_SMEM, (cudaStream_t)stream, c);
     return check_launch("tc_attn_bwd(cols)");
 }
 

@@ -212,13 +212,16 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                            // layout: SWIZZLE_128B
     return d;
 }
-// Instruction descriptor: D fp32, A/B bf16, both K-major, M x N tile
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+// Instruction descriptor (kind::f16): D fp32, M x N tile, K-major operands unless bits 15 / 16 (a / b MN-major) are set.
+// Operand formats are per operand: 0 = fp16, 1 = bf16.
+constexpr uint32_t IDESC_A_F16 = 0u, IDESC_A_BF16 = 1u << 7, IDESC_B_F16 = 0u, IDESC_B_BF16 = 1u << 10;
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {       // formats to be OR-ed in
     return (1u << 4)                       // c_format = F32
-           | (1u << 7)                     // a_format = BF16
-           | (1u << 10)                    // b_format = BF16
            | ((uint32_t)(N >> 3) << 17)    // n_dim
            | ((uint32_t)(M >> 4) << 24);   // m_dim
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return make_idesc_mn(M, N) | IDESC_A_BF16 | IDESC_B_BF16;
 }
 
 }  // namespace tc

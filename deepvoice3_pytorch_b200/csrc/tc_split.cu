@@ -10,21 +10,16 @@
 
 namespace dv3 {
 
-struct TapList { int k; int off[8]; };
-
-// x (B,C,T) fp32 -> dropout -> NPL planes in (B,T,Cp) [forward operand] and, for the weight gradient, 2 planes of k
-// time-shifted copies (k,B,C,T): xs[j][b][c][t] = xd[b][c][t + off_j] (zero outside [0,T)).  The shift is baked
-// into the copy because the weight-gradient GEMM contracts over t (its contiguous axis) and a TMA box cannot start
-// at an element offset that is not 16-byte aligned.  32(c) x 32(t) tile per CTA, block (32, 8).
-template <int NPL>
-__global__ void split_input_kernel(const float* __restrict__ x, bf16* __restrict__ btc, bf16* __restrict__ bct,
-                                   int Bn, int C, int Cp, int T, float p,
-                                   const unsigned long long* __restrict__ seed_ptr, unsigned salt,
-                                   const TapList taps) {
+// x (B,C,T) fp32 -> conv-input dropout -> (hi, lo) fp16 planes in (B,T,Cp) [forward operand] and, when wg != NULL, the
+// same values as a bf16 pair [operand of the weight gradient, which multiplies them with bf16 gradient planes:
+// tcgen05 kind::f16 cannot mix fp16 and bf16 operands].  32(c) x 32(t) tile per CTA, block (32, 8).
+__global__ void split_input_kernel(const float* __restrict__ x, bf16* __restrict__ btc, bf16* __restrict__ wg, int Bn,
+                                   int C, int Cp, int T, float p, const unsigned long long* __restrict__ seed_ptr,
+                                   unsigned salt) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     __shared__ float tile[32][33];
     const DropCfg drop = make_drop(p, seed_ptr, salt);
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
-    const size_t bct_plane = (size_t)taps.k * Bn * C * T;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int c = c0 + threadIdx.y + 8 * i, t = t0 + threadIdx.x;
@@ -32,25 +27,18 @@ __global__ void split_input_kernel(const float* __restrict__ x, bf16* __restrict
         if (c < C && t < T) {
             const size_t row = ((size_t)b * C + c) * T;
             v = x[row + t] * drop_scale(drop, (uint32_t)(row + t));
-            if (bct) {
-                for (int j = 0; j < taps.k; ++j) {
-                    const int ts = t + taps.off[j];
-                    float vs = 0.f;
-                    if (ts >= 0 && ts < T) vs = (ts == t) ? v : x[row + ts] * drop_scale(drop, (uint32_t)(row + ts));
-                    split_store<2>(vs, bct, (((size_t)j * Bn + b) * C + c) * T + t, bct_plane);
-                }
-            }
         }
         tile[threadIdx.y + 8 * i][threadIdx.x] = v;
     }
     __syncthreads();
-    if (btc) {
-        const size_t btc_plane = (size_t)Bn * T * Cp;
+    const size_t btc_plane = (size_t)Bn * T * Cp;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
-            if (c < C && t < T)
-                split_store<NPL>(tile[threadIdx.x][threadIdx.y + 8 * i], btc, ((size_t)b * T + t) * Cp + c, btc_plane);
+    for (int i = 0; i < 4; ++i) {
+        const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
+        if (c < C && t < T) {
+            const float v = tile[threadIdx.x][threadIdx.y + 8 * i];
+            split_store<FMT_F16>(v, btc, ((size_t)b * T + t) * Cp + c, btc_plane);
+            if (wg) split_store<FMT_BF16>(v, wg, ((size_t)b * T + t) * Cp + c, btc_plane);
         }
     }
 }
@@ -59,8 +47,9 @@ __global__ void split_input_kernel(const float* __restrict__ x, bf16* __restrict
 // (B,T,2C) [data-gradient operand] and (B,2C,T) [weight-gradient operand]; dbias[2C] += sums over (b,t).
 __global__ void gate_bwd_split_kernel(const float* __restrict__ dy, const float* __restrict__ a,
                                       const float* __restrict__ s, const float* __restrict__ x,
-                                      bf16* __restrict__ btc, bf16* __restrict__ bct, float* __restrict__ dbias,
-                                      int Bn, int C, int T, int mode, int residual) {
+                                      bf16* __restrict__ btc, float* __restrict__ dbias, int Bn, int C, int T, int mode,
+                                      int residual) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     __shared__ float ta[32][33], tb[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
     const float gs = (mode == 0 && residual) ? 0.70710678118654752f : 1.f;
@@ -74,11 +63,6 @@ __global__ void gate_bwd_split_kernel(const float* __restrict__ dy, const float*
             const float g = dy[in] * gs, av = a[in], sv = s[in];
             da = g * sv;
             db = g * ((mode == 0) ? av : (av - x[in])) * sv * (1.f - sv);
-            if (bct) {
-                const size_t oa = ((size_t)b * 2 * C + c) * T + t;
-                split_store<2>(da, bct, oa, plane);
-                split_store<2>(db, bct, oa + (size_t)C * T, plane);
-            }
         }
         ta[threadIdx.y + 8 * i][threadIdx.x] = da;
         tb[threadIdx.y + 8 * i][threadIdx.x] = db;
@@ -92,16 +76,16 @@ __global__ void gate_bwd_split_kernel(const float* __restrict__ dy, const float*
         const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
         if (c < C && t < T) {
             const size_t o = ((size_t)b * T + t) * 2 * C + c;
-            split_store<2>(ta[threadIdx.x][threadIdx.y + 8 * i], btc, o, plane);
-            split_store<2>(tb[threadIdx.x][threadIdx.y + 8 * i], btc, o + C, plane);
+            split_store<FMT_BF16>(ta[threadIdx.x][threadIdx.y + 8 * i], btc, o, plane);
+            split_store<FMT_BF16>(tb[threadIdx.x][threadIdx.y + 8 * i], btc, o + C, plane);
         }
     }
 }
 
 // plain conv backward prologue: g = dy * (relu ? y > 0 : 1) -> 2 planes in (B,T,Cp) and (B,C,T); dbias[C] += sums.
 __global__ void grad_split_kernel(const float* __restrict__ dy, const float* __restrict__ y, bf16* __restrict__ btc,
-                                  bf16* __restrict__ bct, float* __restrict__ dbias, int Bn, int C, int Cp, int T,
-                                  int relu) {
+                                  float* __restrict__ dbias, int Bn, int C, int Cp, int T, int relu) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
 #pragma unroll
@@ -112,7 +96,6 @@ __global__ void grad_split_kernel(const float* __restrict__ dy, const float* __r
             const size_t in = ((size_t)b * C + c) * T + t;
             g = dy[in];
             if (relu && !(y[in] > 0.f)) g = 0.f;
-            if (bct) split_store<2>(g, bct, in, (size_t)Bn * C * T);
         }
         tile[threadIdx.y + 8 * i][threadIdx.x] = g;
         const float sg = warp_sum(g);
@@ -124,8 +107,8 @@ __global__ void grad_split_kernel(const float* __restrict__ dy, const float* __r
         for (int i = 0; i < 4; ++i) {
             const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
             if (c < C && t < T)
-                split_store<2>(tile[threadIdx.x][threadIdx.y + 8 * i], btc, ((size_t)b * T + t) * Cp + c,
-                               (size_t)Bn * T * Cp);
+                split_store<FMT_BF16>(tile[threadIdx.x][threadIdx.y + 8 * i], btc, ((size_t)b * T + t) * Cp + c,
+                                      (size_t)Bn * T * Cp);
         }
     }
 }
@@ -133,18 +116,20 @@ __global__ void grad_split_kernel(const float* __restrict__ dy, const float* __r
 // weight-norm pack: v [R][X][k] fp32, scale[R] = g/||v|| -> two plane sets with element (r,x,j) at
 // r*s_r + x*s_x + j*s_j: outA is written with lanes along (x,j) (choose the set whose unit stride is s_x),
 // outB with lanes along r (unit stride s_r).
-template <int NPLA, int NPLB>
+template <int FMTA, int FMTB>
 __global__ void wn_pack_split_kernel(const float* __restrict__ v, const float* __restrict__ scale,
                                      bf16* __restrict__ outA, long long a_r, long long a_x, long long a_j,
                                      long long a_plane, bf16* __restrict__ outB, long long b_r, long long b_x,
                                      long long b_j, long long b_plane, int R, int X, int k) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     __shared__ float tile[32][33];
-    wn_pack_split_tile<NPLA, NPLB>(v, scale, outA, a_r, a_x, a_j, a_plane, outB, b_r, b_x, b_j, b_plane, R, X, k,
+    wn_pack_split_tile<FMTA, FMTB>(v, scale, outA, a_r, a_x, a_j, a_plane, outB, b_r, b_x, b_j, b_plane, R, X, k,
                                    blockIdx.x, blockIdx.y, tile);
 }
 
 __global__ void wn_norm_kernel2(const float* __restrict__ v, const float* __restrict__ g,
                                 float* __restrict__ inv_norm, float* __restrict__ scale, int R, int L) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     wn_norm_row(v, g, inv_norm, scale, R, L, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31);
 }
 
@@ -157,88 +142,67 @@ extern "C" {
 int dv3_tc_split_input(const float* x, void* btc, int npl, void* bct, int B, int C, int T, int k, int dilation,
                        int causal, float p_drop, const unsigned long long* seed_ptr, unsigned salt, void* stream) {
     DV3_REQUIRE(B <= 65535 && (C + 31) / 32 <= 65535, "tc_split_input: grid too large");
-    DV3_REQUIRE(k >= 1 && k <= 8, "tc_split_input: kernel size %d not in [1,8]", k);
-    DV3_REQUIRE(npl == 2 || npl == 3, "tc_split_input: npl must be 2 or 3");
-    TapList taps;
-    taps.k = k;
-    const int padl = causal ? (k - 1) * dilation : (k - 1) / 2 * dilation;
-    for (int j = 0; j < 8; ++j) taps.off[j] = j < k ? j * dilation - padl : 0;
+    DV3_REQUIRE(npl == 2, "tc_split_input: npl must be 2");
+    (void)k; (void)dilation; (void)causal;
     const int Cp = (C + 7) / 8 * 8;
     dim3 grid((T + 31) / 32, (C + 31) / 32, B);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (npl == 3)
-        split_input_kernel<3><<<grid, dim3(32, 8), 0, st>>>(x, (bf16*)btc, (bf16*)bct, B, C, Cp, T, p_drop, seed_ptr,
-                                                            salt, taps);
-    else
-        split_input_kernel<2><<<grid, dim3(32, 8), 0, st>>>(x, (bf16*)btc, (bf16*)bct, B, C, Cp, T, p_drop, seed_ptr,
-                                                            salt, taps);
+    launch_k(split_input_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, x, (bf16*)btc, (bf16*)bct, B, C, Cp, T, p_drop,
+             seed_ptr, salt);
     return check_launch("tc_split_input");
 }
 
 int dv3_tc_gate_bwd_split(const float* dy, const float* a, const float* s, const float* x, void* btc, void* bct,
                           float* dbias, int B, int C, int T, int mode, int residual, void* stream) {
+    DV3_REQUIRE(bct == nullptr, "tc_gate_bwd_split: bct must be NULL");
     dim3 grid((T + 31) / 32, (C + 31) / 32, B);
-    gate_bwd_split_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dy, a, s, x, (bf16*)btc, (bf16*)bct, dbias,
-                                                                         B, C, T, mode, residual);
+    launch_k(gate_bwd_split_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, dy, a, s, x, (bf16*)btc, dbias, B, C, T,
+             mode, residual);
     return check_launch("tc_gate_bwd_split");
 }
 
 int dv3_tc_grad_split(const float* dy, const float* y, void* btc, void* bct, float* dbias, int B, int C, int T,
                       int relu, void* stream) {
+    DV3_REQUIRE(bct == nullptr, "tc_grad_split: bct must be NULL");
     const int Cp = (C + 7) / 8 * 8;
     dim3 grid((T + 31) / 32, (C + 31) / 32, B);
-    grad_split_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dy, y, (bf16*)btc, (bf16*)bct, dbias, B, C, Cp,
-                                                                     T, relu);
+    launch_k(grad_split_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, dy, y, (bf16*)btc, dbias, B, C, Cp, T, relu);
     return check_launch("tc_grad_split");
 }
 
 // Weight norm + split for a conv weight v (Cout, Cin, k), g [Cout]:
-//   wfwd: [npl][k][Cout][Cinp]  (forward operand: rows co, K = ci)     wbwd: [2][k][Cin][Coutp]  (data gradient)
+//   wfwd: [2][k][Cout][Cinp] fp16 planes (forward operand: rows co, K = ci)
+//   wbwd: [2][k][Cin][Coutp] bf16 planes (data-gradient operand, multiplied with bf16 gradient planes)
 int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wfwd, int npl,
                           void* wbwd, int Cout, int Cin, int k, void* stream) {
-    DV3_REQUIRE(npl == 2 || npl == 3, "tc_weightnorm_fwd: npl must be 2 or 3");
+    DV3_REQUIRE(npl == 2, "tc_weightnorm_fwd: npl must be 2");
     cudaStream_t st = (cudaStream_t)stream;
     const int L = Cin * k;
     const long long Cinp = (Cin + 7) / 8 * 8, Coutp = (Cout + 7) / 8 * 8;
-    wn_norm_kernel2<<<(Cout * 32 + 255) / 256, 256, 0, st>>>(v, g, inv_norm, scale, Cout, L);
+    launch_k(wn_norm_kernel2, (Cout * 32 + 255) / 256, 256, 0, st, v, g, inv_norm, scale, Cout, L);
     if (int e = check_launch("tc_weightnorm_fwd(norm)")) return e;
     dim3 grid((L + 31) / 32, (Cout + 31) / 32);
-    if (npl == 3)
-        wn_pack_split_kernel<3, 2><<<grid, dim3(32, 8), 0, st>>>(v, scale, (bf16*)wfwd, Cinp, 1, (long long)Cout * Cinp,
-                                                              (long long)k * Cout * Cinp, (bf16*)wbwd, 1, Coutp,
-                                                              (long long)Cin * Coutp, (long long)k * Cin * Coutp,
-                                                              Cout, Cin, k);
-    else
-        wn_pack_split_kernel<2, 2><<<grid, dim3(32, 8), 0, st>>>(v, scale, (bf16*)wfwd, Cinp, 1, (long long)Cout * Cinp,
-                                                              (long long)k * Cout * Cinp, (bf16*)wbwd, 1, Coutp,
-                                                              (long long)Cin * Coutp, (long long)k * Cin * Coutp,
-                                                              Cout, Cin, k);
+    launch_k(wn_pack_split_kernel<FMT_F16, FMT_BF16>, grid, dim3(32, 8), 0, st, v, scale, (bf16*)wfwd, Cinp, 1,
+             (long long)Cout * Cinp, (long long)k * Cout * Cinp, (bf16*)wbwd, 1, Coutp, (long long)Cin * Coutp,
+             (long long)k * Cin * Coutp, Cout, Cin, k);
     return check_launch("tc_weightnorm_fwd(pack)");
 }
 
 // ConvTranspose1d(k=2,s=2) weight v (Cin, Cout, 2), g [Cin] (norm over dim 0 = Cin), run as a 1x1 conv with
 // 2*Cout output rows ordered (j, co):
-//   wfwd: [npl][2*Cout][Cinp]  rows (j,co), K = ci        wbwd: [2][Cin][K2p]  rows ci, K = (j,co), K2p = pad8(2*Cout)
+//   wfwd: [2][2*Cout][Cinp] fp16, rows (j,co), K = ci        wbwd: [2][Cin][K2p] bf16, rows ci, K = (j,co)
 int dv3_tc_weightnorm_convt_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wfwd, int npl,
                                 void* wbwd, int Cin, int Cout, void* stream) {
-    DV3_REQUIRE(npl == 2 || npl == 3, "tc_weightnorm_convt_fwd: npl must be 2 or 3");
+    DV3_REQUIRE(npl == 2, "tc_weightnorm_convt_fwd: npl must be 2");
     cudaStream_t st = (cudaStream_t)stream;
     const int L = Cout * 2;
     const long long Cinp = (Cin + 7) / 8 * 8, K2p = (2 * Cout + 7) / 8 * 8;
-    wn_norm_kernel2<<<(Cin * 32 + 255) / 256, 256, 0, st>>>(v, g, inv_norm, scale, Cin, L);
+    launch_k(wn_norm_kernel2, (Cin * 32 + 255) / 256, 256, 0, st, v, g, inv_norm, scale, Cin, L);
     if (int e = check_launch("tc_weightnorm_convt_fwd(norm)")) return e;
     dim3 grid((L + 31) / 32, (Cin + 31) / 32);
     // r = ci, x = co, j: outA (lanes along (x,j)) = wbwd [ci][j*Cout+co] ; outB (lanes along r) = wfwd [(j*Cout+co)][ci]
-    if (npl == 3)
-        wn_pack_split_kernel<2, 3><<<grid, dim3(32, 8), 0, st>>>(v, scale, (bf16*)wbwd, K2p, 1, (long long)Cout,
-                                                                 (long long)Cin * K2p, (bf16*)wfwd, 1, Cinp,
-                                                                 (long long)Cout * Cinp, (long long)2 * Cout * Cinp,
-                                                                 Cin, Cout, 2);
-    else
-        wn_pack_split_kernel<2, 2><<<grid, dim3(32, 8), 0, st>>>(v, scale, (bf16*)wbwd, K2p, 1, (long long)Cout,
-                                                                 (long long)Cin * K2p, (bf16*)wfwd, 1, Cinp,
-                                                                 (long long)Cout * Cinp, (long long)2 * Cout * Cinp,
-                                                                 Cin, Cout, 2);
+    launch_k(wn_pack_split_kernel<FMT_BF16, FMT_F16>, grid, dim3(32, 8), 0, st, v, scale, (bf16*)wbwd, K2p, 1,
+             (long long)Cout, (long long)Cin * K2p, (bf16*)wfwd, 1, Cinp, (long long)Cout * Cinp,
+             (long long)2 * Cout * Cinp, Cin, Cout, 2);
     return check_launch("tc_weightnorm_convt_fwd(pack)");
 }
 

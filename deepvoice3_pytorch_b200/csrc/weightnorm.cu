@@ -11,6 +11,7 @@ namespace dv3 {
 // one warp per row r: inv_norm[r] = 1/||v[r,:]||, scale[r] = g[r]*inv_norm[r]
 __global__ void wn_norm_kernel(const float* __restrict__ v, const float* __restrict__ g,
                                float* __restrict__ inv_norm, float* __restrict__ scale, int R, int L) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= R) return;
     const float* row = v + (size_t)r * L;
@@ -30,6 +31,7 @@ __global__ void wn_pack_kernel(const float* __restrict__ v, const float* __restr
                                float* __restrict__ out1, float* __restrict__ out2, int R, int L, int k,
                                long long s1r, long long s1x, long long s1j, long long s2r, long long s2x,
                                long long s2j) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     __shared__ float tile[32][33];
     const int r0 = blockIdx.y * 32, e0 = blockIdx.x * 32;
     const int lx = threadIdx.x, ly = threadIdx.y;
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(256) wn_bwd_kernel(float* __restrict__ dw_part
                                                      const float* __restrict__ g,
                                                      const float* __restrict__ inv_norm, float* __restrict__ dv,
                                                      float* __restrict__ dg, int R, int L, int accumulate) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     wn_bwd_row(dw_partials, split_stride, nsplit, jmajor_X, v, g, inv_norm, dv, dg, R, L, accumulate, blockIdx.x);
 }
 
@@ -78,9 +81,9 @@ int dv3_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* s
     DV3_REQUIRE(R > 0 && X > 0 && k > 0, "weightnorm_fwd: empty weight");
     const int L = X * k;
     cudaStream_t st = (cudaStream_t)stream;
-    wn_norm_kernel<<<ceil_div(R * 32, 256), 256, 0, st>>>(v, g, inv_norm, scale, R, L);
+    launch_k(wn_norm_kernel, ceil_div(R * 32, 256), 256, 0, st, v, g, inv_norm, scale, R, L);
     if (int e = check_launch("weightnorm_fwd(norm)")) return e;
-    wn_pack_kernel<<<dim3(ceil_div(L, 32), ceil_div(R, 32)), dim3(32, 8), 0, st>>>(
+    launch_k(wn_pack_kernel, dim3(ceil_div(L, 32), ceil_div(R, 32)), dim3(32, 8), 0, st, 
         v, scale, out1, out2, R, L, k, s1r, s1x, s1j, s2r, s2x, s2j);
     return check_launch("weightnorm_fwd(pack)");
 }
@@ -90,7 +93,7 @@ int dv3_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* s
 int dv3_weightnorm_bwd(float* dw_partials, long long split_stride, int nsplit, int tap_major, const float* v,
                        const float* g, const float* inv_norm, float* dv, float* dg, int R, int X, int k,
                        int accumulate, void* stream) {
-    wn_bwd_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(
+    launch_k(wn_bwd_kernel, R, 256, 0, (cudaStream_t)stream, 
         dw_partials, split_stride, nsplit, tap_major ? X : 0, v, g, inv_norm, dv, dg, R, X * k, accumulate);
     return check_launch("weightnorm_bwd");
 }

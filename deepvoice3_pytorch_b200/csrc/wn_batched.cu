@@ -26,6 +26,7 @@ __device__ __forceinline__ int find_entry(const Dv3WnEntry* __restrict__ tab, in
 }
 
 __global__ void __launch_bounds__(256) wn_norm_batched_kernel(const Dv3WnEntry* __restrict__ tab, int n) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int ei = find_entry<0>(tab, n, blockIdx.x);
     const Dv3WnEntry e = tab[ei];
     const int lb = blockIdx.x - e.blk_norm;
@@ -34,13 +35,14 @@ __global__ void __launch_bounds__(256) wn_norm_batched_kernel(const Dv3WnEntry* 
 
 // same layouts as dv3_tc_weightnorm_fwd (npl = 2): wfwd [2][k][Cout][Cinp], wbwd [2][k][Cin][Coutp]
 __global__ void __launch_bounds__(256) wn_pack_batched_kernel(const Dv3WnEntry* __restrict__ tab, int n) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     __shared__ float tile[32][33];
     const int ei = find_entry<1>(tab, n, blockIdx.x);
     const Dv3WnEntry e = tab[ei];
     const int lb = blockIdx.x - e.blk_pack;
     const int by = lb / e.pack_gx, bx = lb - by * e.pack_gx;
     const long long Cinp = (e.Cin + 7) / 8 * 8, Coutp = (e.Cout + 7) / 8 * 8;
-    wn_pack_split_tile<2, 2>(e.v, e.scale, (bf16*)e.wfwd, Cinp, 1, (long long)e.Cout * Cinp,
+    wn_pack_split_tile<FMT_F16, FMT_BF16>(e.v, e.scale, (bf16*)e.wfwd, Cinp, 1, (long long)e.Cout * Cinp,
                              (long long)e.k * e.Cout * Cinp, (bf16*)e.wbwd, 1, Coutp, (long long)e.Cin * Coutp,
                              (long long)e.k * e.Cin * Coutp, e.Cout, e.Cin, e.k, bx, by, tile);
 }
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(256) wn_pack_batched_kernel(const Dv3WnEntry* 
 // tap-major partials [split][j][Cout][Cin] (what dv3_tc_wgrad_mn writes) -> dv, dg
 __global__ void __launch_bounds__(256) wn_bwd_batched_kernel(const Dv3WnEntry* __restrict__ tab, int n,
                                                              int accumulate) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int ei = find_entry<2>(tab, n, blockIdx.x);
     const Dv3WnEntry e = tab[ei];
     const int r = blockIdx.x - e.blk_bwd;
@@ -66,15 +69,15 @@ int dv3_tc_weightnorm_fwd_batched(const Dv3WnEntry* table_dev, int n, int norm_b
                                   void* stream) {
     DV3_REQUIRE(n > 0 && norm_blocks > 0 && pack_blocks > 0, "tc_weightnorm_fwd_batched: empty table");
     cudaStream_t st = (cudaStream_t)stream;
-    wn_norm_batched_kernel<<<norm_blocks, 256, 0, st>>>(table_dev, n);
+    launch_k(wn_norm_batched_kernel, norm_blocks, 256, 0, st, table_dev, n);
     if (int e = check_launch("tc_weightnorm_fwd_batched(norm)")) return e;
-    wn_pack_batched_kernel<<<pack_blocks, dim3(32, 8), 0, st>>>(table_dev, n);
+    launch_k(wn_pack_batched_kernel, pack_blocks, dim3(32, 8), 0, st, table_dev, n);
     return check_launch("tc_weightnorm_fwd_batched(pack)");
 }
 
 int dv3_weightnorm_bwd_batched(const Dv3WnEntry* table_dev, int n, int bwd_blocks, int accumulate, void* stream) {
     DV3_REQUIRE(n > 0 && bwd_blocks > 0, "weightnorm_bwd_batched: empty table");
-    wn_bwd_batched_kernel<<<bwd_blocks, 256, 0, (cudaStream_t)stream>>>(table_dev, n, accumulate);
+    launch_k(wn_bwd_batched_kernel, bwd_blocks, 256, 0, (cudaStream_t)stream, table_dev, n, accumulate);
     return check_launch("weightnorm_bwd_batched");
 }
 

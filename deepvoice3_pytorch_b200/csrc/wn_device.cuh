@@ -8,17 +8,13 @@ namespace dv3 {
 
 typedef __nv_bfloat16 bf16;
 
-template <int NPL>
+// x -> (hi, lo) planes in format FMT (common.cuh: FMT_F16 forward operands, FMT_BF16 gradients)
+template <int FMT>
 __device__ __forceinline__ void split_store(float v, bf16* __restrict__ base, size_t idx, size_t plane_stride) {
-    const bf16 h = __float2bfloat16_rn(v);
-    base[idx] = h;
-    float r = v - __bfloat162float(h);
-    const bf16 m = __float2bfloat16_rn(r);
-    base[plane_stride + idx] = m;
-    if (NPL == 3) {
-        r -= __bfloat162float(m);
-        base[2 * plane_stride + idx] = __float2bfloat16_rn(r);
-    }
+    uint16_t h, l;
+    split_pair<FMT>(v, h, l);
+    reinterpret_cast<uint16_t*>(base)[idx] = h;
+    reinterpret_cast<uint16_t*>(base)[plane_stride + idx] = l;
 }
 
 // one warp per row r: inv_norm[r] = 1/||v[r,:]||, scale[r] = g[r]*inv_norm[r]

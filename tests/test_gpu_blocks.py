@@ -213,23 +213,3 @@ def test_convblock_dropout_statistics_and_consistency(math, C, monkeypatch):
     # eval: no dropout
     y3 = ops.convblock(x, v, g, bias, None, k, 1, False, ops.MODE_GLU, False, p_drop=p, training=False)
     close(y3, 0.5 * x, rtol=2e-4, atol=1e-6)
-
-
-@pytest.mark.gpu
-def test_cta_pair_kernels_match_exact_fp32():
-    """The opt-in CTA-pair kernels (tcgen05 cta_group::2, DV3_TC_PAIR=2 forces them for every even batch) give the
-    same forward / data-gradient results as the exact-fp32 kernels, to the split-bf16 accuracy.  The knob is read once
-    per process, so this runs tools/tc_debug.py in a child process."""
-    import os
-    import re
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, DV3_TC_PAIR="2")
-    for case in ("2", "5", "8"):                  # (2,128,128,k3) (4,512,128,k3,d27) (16,512,800,k3)
-        out = subprocess.run([sys.executable, os.path.join(root, "tools", "tc_debug.py"), case], env=env,
-                             capture_output=True, text=True, timeout=300)
-        assert out.returncode == 0, out.stdout + out.stderr
-        line = out.stdout.strip().splitlines()[-1]
-        errs = [float(v) for v in re.findall(r"=(\d\.\d+e[-+]\d+)", line)]
-        assert len(errs) == 5 and max(errs) < 3e-5, line
