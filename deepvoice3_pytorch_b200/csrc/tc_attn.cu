@@ -94,38 +94,65 @@ __device__ __forceinline__ void load8(const float* __restrict__ row, int c0, int
     }
 }
 
+// The staging loops below issue the global loads of UNR groups (2 x float4 each) before the first conversion / shared
+// store, so a thread has UNR x 32 bytes in flight instead of one group (the one-group-at-a-time version was latency
+// bound: 60-140 us per launch for ~1 MB of operands).
+constexpr int ST_UNR = 4;
+
 // Stage an MN-major operand chunk: 64 contraction rows (global rows r0 .. r0+64 of a (nrows, ncols) matrix, row stride
 // ld) x NCH*64 columns starting at column c_base; two planes (hi at dst, lo at dst + plane_bytes); chunk stride 8 KB.
 template <int NCH>
 __device__ __forceinline__ void stage_mn(uint8_t* dst, uint32_t plane_bytes, const float* __restrict__ src, long long ld,
                                          int r0, int nrows, int c_base, int ncols, bool vec_ok, int tid, int nthreads) {
     constexpr int GROUPS_PER_ROW = NCH * 8;                // 16-byte chunks (8 elements) per row
-    for (int g = tid; g < 64 * GROUPS_PER_ROW; g += nthreads) {
-        const int r = g / GROUPS_PER_ROW, cg = g - r * GROUPS_PER_ROW;
-        const int h = cg >> 3, c = cg & 7;
-        float x[8];
-        load8(src + (long long)(r0 + r) * ld, c_base + cg * 8, ncols, r0 + r < nrows, vec_ok, x);
-        uint4 hi, lo;
-        split8(x, hi, lo);
-        const uint32_t off = (uint32_t)h * 8192u + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst + off) = hi;
-        *reinterpret_cast<uint4*>(dst + plane_bytes + off) = lo;
+    constexpr int TOTAL = 64 * GROUPS_PER_ROW;
+    for (int g0 = tid; g0 < TOTAL; g0 += nthreads * ST_UNR) {
+        float x[ST_UNR][8];
+#pragma unroll
+        for (int u = 0; u < ST_UNR; ++u) {
+            const int g = g0 + u * nthreads;
+            const int r = g / GROUPS_PER_ROW, cg = g - r * GROUPS_PER_ROW;
+            load8(src + (long long)(r0 + r) * ld, c_base + cg * 8, ncols, g < TOTAL && r0 + r < nrows, vec_ok, x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < ST_UNR; ++u) {
+            const int g = g0 + u * nthreads;
+            if (g >= TOTAL) break;
+            const int r = g / GROUPS_PER_ROW, cg = g - r * GROUPS_PER_ROW;
+            const int h = cg >> 3, c = cg & 7;
+            uint4 hi, lo;
+            split8(x[u], hi, lo);
+            const uint32_t off = (uint32_t)h * 8192u + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst + off) = hi;
+            *reinterpret_cast<uint4*>(dst + plane_bytes + off) = lo;
+        }
     }
 }
 
-// Stage a K-major operand: NROWS rows (global rows r0.., row stride ld) x 64 contraction columns starting at c_base.
+// Stage a K-major operand: nrows_tile rows (global rows r0.., row stride ld) x 64 contraction columns starting at c_base.
 __device__ __forceinline__ void stage_k(uint8_t* dst, uint32_t plane_bytes, const float* __restrict__ src, long long ld,
                                         int r0, int nrows_valid, int nrows_tile, int c_base, int ncols, bool vec_ok,
                                         int tid, int nthreads) {
-    for (int g = tid; g < nrows_tile * 8; g += nthreads) {
-        const int r = g >> 3, c = g & 7;
-        float x[8];
-        load8(src + (long long)(r0 + r) * ld, c_base + c * 8, ncols, r0 + r < nrows_valid, vec_ok, x);
-        uint4 hi, lo;
-        split8(x, hi, lo);
-        const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst + off) = hi;
-        *reinterpret_cast<uint4*>(dst + plane_bytes + off) = lo;
+    const int total = nrows_tile * 8;
+    for (int g0 = tid; g0 < total; g0 += nthreads * ST_UNR) {
+        float x[ST_UNR][8];
+#pragma unroll
+        for (int u = 0; u < ST_UNR; ++u) {
+            const int g = g0 + u * nthreads;
+            const int r = g >> 3, c = g & 7;
+            load8(src + (long long)(r0 + r) * ld, c_base + c * 8, ncols, g < total && r0 + r < nrows_valid, vec_ok, x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < ST_UNR; ++u) {
+            const int g = g0 + u * nthreads;
+            if (g >= total) break;
+            const int r = g >> 3, c = g & 7;
+            uint4 hi, lo;
+            split8(x[u], hi, lo);
+            const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst + off) = hi;
+            *reinterpret_cast<uint4*>(dst + plane_bytes + off) = lo;
+        }
     }
 }
 
@@ -388,25 +415,32 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_cols_kernel(const __grid_c
         // B operands: 64 query rows of (Td,Ts); Pd = P * dropout mask regenerated from the element index
         {
             uint8_t* dst = smem + 65536;
-            for (int g = tid; g < 64 * 16; g += AT_THREADS) {
-                const int r = g >> 4, cg = g & 15, h = cg >> 3, c = cg & 7;
-                const int t = kc * 64 + r;
-                float x[8], y[8];
-                load8(P + (long long)t * Ts, cg * 8, Ts, t < Td, vec_ts, x);
-                load8(dS + (long long)t * Ts, cg * 8, Ts, t < Td, vec_ts, y);
-                if (drop.on) {
-                    const size_t idx0 = ((size_t)b * Td + t) * Ts + cg * 8;
+            for (int g0 = tid; g0 < 64 * 16; g0 += AT_THREADS * 2) {
+                float x[2][8], y[2][8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) x[i] *= drop_scale(drop, (uint32_t)(idx0 + i));
+                for (int u = 0; u < 2; ++u) {
+                    const int g = g0 + u * AT_THREADS, r = g >> 4, cg = g & 15, t = kc * 64 + r;
+                    load8(P + (long long)t * Ts, cg * 8, Ts, t < Td, vec_ts, x[u]);
+                    load8(dS + (long long)t * Ts, cg * 8, Ts, t < Td, vec_ts, y[u]);
                 }
-                uint4 hi, lo;
-                const uint32_t off = (uint32_t)h * 8192u + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-                split8(x, hi, lo);
-                *reinterpret_cast<uint4*>(dst + off) = hi;
-                *reinterpret_cast<uint4*>(dst + 16384 + off) = lo;
-                split8(y, hi, lo);
-                *reinterpret_cast<uint4*>(dst + 32768 + off) = hi;
-                *reinterpret_cast<uint4*>(dst + 49152 + off) = lo;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int g = g0 + u * AT_THREADS, r = g >> 4, cg = g & 15, h = cg >> 3, c = cg & 7;
+                    const int t = kc * 64 + r;
+                    if (drop.on) {
+                        const size_t idx0 = ((size_t)b * Td + t) * Ts + cg * 8;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) x[u][i] *= drop_scale(drop, (uint32_t)(idx0 + i));
+                    }
+                    uint4 hi, lo;
+                    const uint32_t off = (uint32_t)h * 8192u + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+                    split8(x[u], hi, lo);
+                    *reinterpret_cast<uint4*>(dst + off) = hi;
+                    *reinterpret_cast<uint4*>(dst + 16384 + off) = lo;
+                    split8(y[u], hi, lo);
+                    *reinterpret_cast<uint4*>(dst + 32768 + off) = hi;
+                    *reinterpret_cast<uint4*>(dst + 49152 + off) = lo;
+                }
             }
         }
         fence_proxy_async();

@@ -155,7 +155,7 @@ __device__ __forceinline__ void epi_emit(EpiStage& es, int row, const float* v, 
             h[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
             l[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
         }
-        const uint32_t off = (uint32_t)row * 64u + (uint32_t)((j ^ ((row >> 1) & 3)) << 4);
+        const uint32_t off = (uint32_t)row * 64u + (uint32_t)((j ^ ((row >> 1) & 3)) << 4);   // SWIZZLE_64B
         *reinterpret_cast<uint4*>(buf + off) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(buf + 8192 + off) = make_uint4(l[0], l[1], l[2], l[3]);
     }

@@ -67,6 +67,11 @@ class Encoder(nn.Module):
                              dropout=dropout))
         self.convolutions = nn.ModuleList(layers)
 
+    def grad_bucket_split(self):
+        """Index into ``convolutions``: the layers from here on form the "encoder_hi" gradient bucket of the
+        data-parallel step (their backward finishes first; the encoder holds 60 % of the parameters)."""
+        return len(self.convolutions) * 2 // 5
+
     def forward(self, text_sequences, text_positions=None, lengths=None, speaker_embed=None):
         """-> keys, values, both (B, T_text, embed_dim) (reference deepvoice3.py:69-105)."""
         assert self.n_speakers == 1 or speaker_embed is not None
@@ -77,7 +82,8 @@ class Encoder(nn.Module):
             speaker_embed_btc = ops.dropout(speaker_embed_btc, self.dropout, self.training)
             x = x + F.softsign(self.speaker_fc1(speaker_embed_btc))
         input_embedding = x
-        x = run_conv_stack(self.convolutions, ops.transpose12(x), speaker_embed_btc)
+        x = run_conv_stack(self.convolutions, ops.transpose12(x), speaker_embed_btc,
+                           boundaries={self.grad_bucket_split(): "encoder_hi"})
         keys = ops.transpose12(x)
         if speaker_embed_btc is not None:
             keys = keys + F.softsign(self.speaker_fc2(speaker_embed_btc))

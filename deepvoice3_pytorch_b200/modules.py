@@ -210,15 +210,19 @@ def _consumer_dropout(f):
     return None
 
 
-def run_conv_stack(layers, x, speaker_embed_btc=None):
+def run_conv_stack(layers, x, speaker_embed_btc=None, boundaries=None):
     """Run a ModuleList/Sequential of [Conv1d | ReLU | Sigmoid | ConvTranspose1d | Conv1dGLU | HighwayConv1d]
     on x (B, C, T), fusing every ``Conv1d -> ReLU`` pair into one kernel launch.  Inside the stack every tensor has
     exactly one consumer -- the next layer -- which is what lets the tensor-core epilogues prepare the next layer's
-    operand planes (forward) and run the previous layer's gate / ReLU backward (data gradient): ops.Chain."""
+    operand planes (forward) and run the previous layer's gate / ReLU backward (data gradient): ops.Chain.
+    boundaries: {layer index: tag} -- the input of that layer is an ops.grad_boundary (its gradient being ready means
+    the parameter gradients of layers[index:] are final)."""
     layers = list(layers)
     i, follows = 0, False
     while i < len(layers):
         f = layers[i]
+        if boundaries and i in boundaries:
+            x = ops.grad_boundary(x, boundaries[i])
         fuse_relu = isinstance(f, _Conv1d) and i + 1 < len(layers) and isinstance(layers[i + 1], nn.ReLU)
         nxt = i + (2 if fuse_relu else 1)
         emit_p = _consumer_dropout(layers[nxt]) if nxt < len(layers) else None

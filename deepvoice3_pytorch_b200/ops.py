@@ -13,13 +13,14 @@ from ._lib import lib, Dv3Error
 
 MODE_GLU, MODE_HIGHWAY = 0, 1
 
-# Arithmetic of the ConvBlock contractions:
-#   "fp32"   exact-fp32 CUDA-core kernels (csrc/conv.cu)
-#   "tc"     tcgen05 tensor cores with split-bf16 operands, hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM
-#            (csrc/tc_gemm.cu): every output / gradient of a block within ~1e-5 of the exact-fp32 kernels.  Shapes the
-#            tensor-core kernels do not cover (C % 128 != 0, T % 8 != 0, tiny GEMMs) still run on the fp32 kernels.
-#            ("bf16x3" is accepted as an alias.)
-conv_math = os.environ.get("DV3_CONV_MATH", "fp32")
+# Arithmetic of the ConvBlock / conv / attention contractions:
+#   "tc"     (default) tcgen05 tensor cores, every fp32 operand split into a 16-bit (hi, lo) pair, hi*hi + hi*lo + lo*hi
+#            with fp32 accumulation in TMEM (csrc/tc_gemm.cu, tc_attn.cu): fp16 pairs (22-bit operands) in the forward
+#            GEMMs, bf16 pairs in the gradient GEMMs.  Full-depth preset models match the fp32 oracle at rtol 1e-3 /
+#            atol 1e-4 (tests/test_gpu_models.py).  Shapes the tensor-core kernels do not cover (C % 128 != 0, tiny
+#            GEMMs) run on the exact-fp32 kernels automatically.  ("bf16x3" is accepted as an alias.)
+#   "fp32"   exact-fp32 CUDA-core kernels everywhere (csrc/conv.cu, bgemm.cu): ~7x slower, the strict reference mode.
+conv_math = os.environ.get("DV3_CONV_MATH", "tc")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -154,6 +155,23 @@ def _wn_conv_fwd(v, g):
 # removes one ``grad += new`` elementwise kernel per parameter per step (~130 launches).  Off by default: plain
 # autograd semantics (Functions return dv, dg, dbias).
 grad_sink = False
+
+
+# Gradient-bucket boundaries (set by train_step.TrainStep in data-parallel runs): ``grad_boundary(x, tag)`` marks a tensor
+# whose gradient, once computed, proves that every parameter gradient of the layers AFTER it is final -- the training
+# step then starts the NCCL all-reduce of that parameter bucket while the rest of the backward pass still runs.
+grad_boundary_cb = None
+
+
+def grad_boundary(x, tag):
+    if grad_boundary_cb is not None and x.requires_grad:
+        cb = grad_boundary_cb
+
+        def _hook(grad, tag=tag, cb=cb):
+            cb(tag)
+            return None
+        x.register_hook(_hook)
+    return x
 
 
 # Batched weight norm (weight_bank.WeightBank), installed by train_step.TrainStep for the duration of one
@@ -299,8 +317,13 @@ def _pad8(n):
 # fuse_bwd: the data-gradient GEMM of the consumer applies the producer's backward (gate / ReLU) in its epilogue and
 #           emits the producer's gradient planes + bias-gradient sums -> no dv3_tc_gate_bwd_split / dv3_tc_grad_split.
 # Both need the caller (modules.run_conv_stack) to state that the tensor has exactly ONE consumer.
-fuse_fwd = os.environ.get("DV3_FUSE_FWD", "1") == "1"
-fuse_bwd = os.environ.get("DV3_FUSE_BWD", "1") == "1"
+# Both are OFF by default: measured on the B200 (profiles/r02_fusion_ab.txt) the fused step is SLOWER (7.26 vs 6.34 ms,
+# forward fusion alone 6.45): the separate split / gate-backward kernels stream at HBM speed with full occupancy, while
+# inside the GEMM the same work is done by the 4 epilogue warps of each SM (latency bound), and at C = 256 the fused
+# data-gradient epilogue of a 128x128 tile takes longer than the tile's MMAs.  Kept opt-in because the arithmetic is
+# bit-identical (tests/test_gpu_fusion.py) and the trade flips for wider layers.
+fuse_fwd = os.environ.get("DV3_FUSE_FWD", "0") == "1"
+fuse_bwd = os.environ.get("DV3_FUSE_BWD", "0") == "1"
 
 POST_GLU, POST_HIGHWAY, POST_RELU, POST_IDENT = 1, 2, 3, 4
 
@@ -353,12 +376,14 @@ def _fuse_struct(emit=None, rec=None, dbias=None):
     return ctypes.byref(f), f
 
 
-def _new_planes(emit_p, training, B, T, C, dev):
-    """Planes buffer + dropout identity for a consumer with input dropout ``emit_p`` (None: nothing to emit)."""
+def _new_planes(emit_p, training, B, T, C, dev, need_wg):
+    """Planes buffer + dropout identity for a consumer with input dropout ``emit_p`` (None: nothing to emit).
+    need_wg: also the bf16 pair the consumer's weight gradient reads (the producer passes its own need-backward flag:
+    grad mode is off inside autograd.Function.forward, so it cannot be asked here)."""
     if emit_p is None or not fuse_fwd:
         return None
     p, seed_t, salt = _drop_args(emit_p, training, dev)
-    wg = torch.empty(2, B, T, _pad8(C), device=dev, dtype=torch.bfloat16) if torch.is_grad_enabled() else None
+    wg = torch.empty(2, B, T, _pad8(C), device=dev, dtype=torch.bfloat16) if need_wg else None
     return Planes(torch.empty(2, B, T, _pad8(C), device=dev, dtype=torch.float16), wg, C, p, seed_t, salt)
 
 
@@ -414,12 +439,15 @@ class _ConvBlockTCFn(torch.autograd.Function):
             wfwd = torch.empty(2, k, 2 * C, C, device=dev, dtype=torch.float16)
             wbwd = torch.empty(2, k, C, 2 * C, device=dev, dtype=bf)
         p_eff = float(p_drop) if (training and p_drop > 0.0) else 0.0
-        if _usable(xh, C, B, T, p_eff) and (xh.wg is not None or not need_bwd):
-            x_btc, x_wg = xh.t, xh.wg                    # the producer already applied our dropout
+        usable = _usable(xh, C, B, T, p_eff)
+        if usable:                                       # the producer drew our dropout identity (salt order unchanged)
             p, seed_t, salt = xh.p, xh.seed_t, xh.salt
-            split = False
         else:
             p, seed_t, salt = _drop_args(p_drop, training, dev)
+        if usable and (xh.wg is not None or not need_bwd):
+            x_btc, x_wg = xh.t, xh.wg                    # ... and already applied it to the planes it wrote
+            split = False
+        else:
             x_btc = torch.empty(2, B, T, C, device=dev, dtype=torch.float16)        # forward operand (fp16 pair)
             x_wg = torch.empty(2, B, T, C, device=dev, dtype=bf) if need_bwd else None  # weight-gradient operand
             split = True
@@ -438,7 +466,7 @@ class _ConvBlockTCFn(torch.autograd.Function):
                      seed_ptr, salt, _stream())
         if side is not None:
             side.join()
-        emit = _new_planes(emit_p, training, B, T, C, dev)
+        emit = _new_planes(emit_p, training, B, T, C, dev, need_bwd)
         fptr, _keep = _fuse_struct(emit=emit)
         lib.call("dv3_tc_convblock_fwd", _p(x_btc), _p(wfwd), 2, _p(bias), _p(spk), _p(x), _p(y), _p(a), _p(s),
                  B, C, T, k, dilation, int(causal), mode, int(residual), fptr, _stream())
@@ -564,7 +592,7 @@ class _Conv1dTCFn(torch.autograd.Function):
                      None, 0, _stream())
         if side is not None:
             side.join()
-        emit = _new_planes(emit_p, training, B, T, Cout, dev)
+        emit = _new_planes(emit_p, training, B, T, Cout, dev, need_bwd)
         fptr, _keep = _fuse_struct(emit=emit)
         lib.call("dv3_tc_conv", _p(x_btc), _p(wfwd), 2, _p(y), B, Cin, Cout, T, k, dilation, int(causal), 0,
                  _p(bias), int(relu), 0.0, None, 0, 0, None, None, 0.0, fptr, _stream())
@@ -1092,6 +1120,9 @@ class _AttentionCoreFn(torch.autograd.Function):
         return dq, dk, dv, None, None, None
 
 
+tc_attention = os.environ.get("DV3_TC_ATTN", "1") == "1"      # 0: attention on the exact-fp32 bgemm + softmax kernels
+
+
 class _AttentionTCFn(torch.autograd.Function):
     """The same contract on the fused tcgen05 kernels (csrc/tc_attn.cu): one launch forward, two backward."""
 
@@ -1133,6 +1164,7 @@ def attention_core(q, k, v, mask=None, p_drop=0.0, training=False):
     if mask is not None:
         mask = mask.to(torch.uint8).contiguous()
     B, E, Td = q.shape
-    tc = conv_math in ("tc", "bf16x3") and q.is_cuda and lib.raw("dv3_tc_attn_supported")(B, E, Td, k.shape[2])
+    tc = (conv_math in ("tc", "bf16x3") and tc_attention and q.is_cuda and
+          lib.raw("dv3_tc_attn_supported")(B, E, Td, k.shape[2]))
     fn = _AttentionTCFn if tc else _AttentionCoreFn
     return fn.apply(_c(q), _c(k), _c(v), mask, float(p_drop), bool(training))

@@ -198,11 +198,55 @@ class ParameterArena:
                 if id(t) not in inside:
                     dist.broadcast(t.data, src)
 
-    def all_reduce_grads(self):
-        """The one exchange step of the data-parallel path: sum the flat gradient arena over all ranks (NCCL over
-        NVLink on GPUs; gloo in the CPU tests).  The 1/world average is applied by the optimizer (hyper[3])."""
+    def all_reduce_grads(self, ranges=None):
+        """The exchange step of the data-parallel path: sum the flat gradient arena (or the given [lo, hi) slices of
+        it) over all ranks (NCCL over NVLink on GPUs; gloo in the CPU tests).  The 1/world average is applied by the
+        optimizer (hyper[3])."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grad)
+            if ranges is None:
+                dist.all_reduce(self.grad)
+            else:
+                for lo, hi in ranges:
+                    if hi > lo:
+                        dist.all_reduce(self.grad[lo:hi])
+
+    def range_of(self, params):
+        """[lo, hi) of the arena slice holding ``params`` (must be consecutive arena entries), or None if empty."""
+        ids = {id(p) for p in params}
+        idx = [i for i, p in enumerate(self.params) if id(p) in ids]
+        if not idx:
+            return None
+        assert idx == list(range(idx[0], idx[-1] + 1)), "bucket parameters are not contiguous in the arena"
+        last = idx[-1]
+        return self.offsets[idx[0]], self.offsets[last] + (self.params[last].numel() + 3) // 4 * 4
+
+
+def gradient_buckets(model, arena):
+    """Bucket plan of the overlapped gradient exchange.  The backward pass finishes the post-net first, then the
+    decoder, then the encoder from its last layer to its first (the encoder holds ~60 % of the parameters), so:
+      "postnet"     everything under model.postnet        -- final when d(loss)/d(postnet input) exists
+      "encoder_hi"  encoder.convolutions[split:]          -- final when the gradient entering layer `split` exists
+      "rest"        all other slices (decoder, first encoder layers, embeddings): reduced after backward()
+    -> ({tag: (lo, hi)}, [rest ranges])."""
+    tagged = {}
+    post = arena.range_of(list(model.postnet.parameters())) if hasattr(model, "postnet") else None
+    if post:
+        tagged["postnet"] = post
+    enc = getattr(getattr(model, "seq2seq", None), "encoder", None)
+    if enc is not None and hasattr(enc, "grad_bucket_split") and hasattr(enc, "convolutions"):
+        ps = [p for m in list(enc.convolutions)[enc.grad_bucket_split():] for p in m.parameters()]
+        r = arena.range_of(ps)
+        if r:
+            tagged["encoder_hi"] = r
+    cuts = sorted(tagged.values())
+    rest, pos = [], 0
+    for lo, hi in cuts:
+        if lo > pos:
+            rest.append((pos, lo))
+        pos = max(pos, hi)
+    if pos < arena.numel:
+        rest.append((pos, arena.numel))
+    return tagged, rest
 
 
 class FlatAdam:
@@ -324,6 +368,15 @@ class TrainStep:
             weight_bank = os.environ.get("DV3_WEIGHT_BANK", "1") == "1"
         self.bank = WeightBank() if weight_bank else None
         self.arena.broadcast(model)             # replicas start from rank 0's weights (no-op for world == 1)
+        # overlapped gradient exchange (world > 1): buckets are all-reduced on a communication stream as soon as the
+        # backward pass has finished them; only the last ("rest") bucket is exposed
+        self.buckets, self.rest_ranges = gradient_buckets(model, self.arena)
+        self.overlap_comm = self.world > 1 and os.environ.get("DV3_OVERLAP_COMM", "1") == "1" and \
+            self.arena.flat.is_cuda
+        self._comm = torch.cuda.Stream(device=self.arena.flat.device) if self.overlap_comm else None
+        self._reduced = set()
+        # capture the NCCL collectives inside the step's CUDA graph (so clip + Adam stay in the graph too)
+        self.graph_comm = self.overlap_comm and os.environ.get("DV3_GRAPH_COMM", "1") == "1"
 
     # -- checkpointing: the reference's checkpoint keys (train.py:787-810) ---------------------------------
     def state_dict(self, global_epoch=0):
@@ -343,7 +396,9 @@ class TrainStep:
     def _forward_backward(self, batch):
         self.arena.zero_grad()
         ops.grad_sink = True          # kernels accumulate parameter gradients straight into the arena
-        ops.weight_bank = self.bank   # weight norm of all layers: 2 launches up front, 1 after the backward pass
+        ops.weight_bank = self.bank   # weight norm of all layers: 2 launches up front, 1 per bucket in the backward
+        ops.grad_boundary_cb = self._bucket_ready if self.overlap_comm else None
+        self._reduced = set()
         try:
             if self.bank is not None:
                 self.bank.begin_step()
@@ -351,8 +406,23 @@ class TrainStep:
         finally:
             ops.grad_sink = False
             ops.weight_bank = None
+            ops.grad_boundary_cb = None
             if self.bank is not None:
                 self.bank.end_step()
+
+    def _bucket_ready(self, tag):
+        """Called from the backward pass (ops.grad_boundary hook): the parameter gradients of bucket ``tag`` are final
+        -- finish their weight-norm backward and start their all-reduce on the communication stream."""
+        rng = self.buckets.get(tag)
+        if rng is None or tag in self._reduced:
+            return
+        self._reduced.add(tag)
+        if self.bank is not None:
+            self.bank.end_backward()
+        main = torch.cuda.current_stream()
+        self._comm.wait_stream(main)
+        with torch.cuda.stream(self._comm):
+            self.arena.all_reduce_grads([rng])
 
     def _forward_backward_inner(self, batch):
         outs = self.model(batch["x"], batch["mel"], speaker_ids=batch.get("speaker_ids"),
@@ -365,7 +435,16 @@ class TrainStep:
         return loss.detach()
 
     def _exchange_and_update(self):
-        self.arena.all_reduce_grads()                   # sum; the 1/world average is folded into hyper[3]
+        """Gradient exchange (sum; the 1/world average is folded into hyper[3]) + clip + Adam."""
+        if self.overlap_comm:
+            main = torch.cuda.current_stream()
+            self._comm.wait_stream(main)
+            with torch.cuda.stream(self._comm):         # buckets whose boundary never fired + everything else
+                pending = [r for t, r in self.buckets.items() if t not in self._reduced]
+                self.arena.all_reduce_grads(pending + self.rest_ranges)
+            main.wait_stream(self._comm)
+        else:
+            self.arena.all_reduce_grads()
         self.opt.apply()          # (fresh dropout masks per step: the model's forward draws a new seed itself)
 
     # -- public -------------------------------------------------------------------------------
@@ -396,20 +475,27 @@ class TrainStep:
                 seed0 = ops.rng.base.clone()
                 for _ in range(2):
                     self._forward_backward(self._static)
+                    if self.world > 1 and self.overlap_comm:    # NCCL communicators / bucket tables exist before capture
+                        pend = [r for t, r in self.buckets.items() if t not in self._reduced]
+                        with torch.cuda.stream(self._comm):
+                            self._comm.wait_stream(s)
+                            self.arena.all_reduce_grads(pend + self.rest_ranges)
+                        s.wait_stream(self._comm)
                 ops.rng.base.copy_(seed0)           # the warm-up passes do not consume dropout seeds
             torch.cuda.current_stream().wait_stream(s)
             self._graph = torch.cuda.CUDAGraph()
             n0 = lib.raw("dv3_launch_count")()
+            capture_all = self.world == 1 or self.graph_comm
             with torch.cuda.graph(self._graph):
                 self._loss = self._forward_backward(self._static)
-                if self.world == 1:
+                if capture_all:                     # NCCL all-reduces are captured as graph nodes on the comm stream
                     self._exchange_and_update()
-            self.launches_per_step = int(lib.raw("dv3_launch_count")() - n0) + (2 if self.world > 1 else 0)
+            self.launches_per_step = int(lib.raw("dv3_launch_count")() - n0) + (0 if capture_all else 2)
         for k, v in batch.items():
             if torch.is_tensor(v):
                 self._static[k].copy_(v, non_blocking=True)
         self._graph.replay()
-        if self.world > 1:
+        if self.world > 1 and not self.graph_comm:
             self._exchange_and_update()
         return self._loss
 

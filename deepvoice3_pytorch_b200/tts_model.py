@@ -92,6 +92,7 @@ class MultiSpeakerTTSModel(nn.Module):
                                                          frame_positions, input_lengths)
             mel = mel.reshape(batch, -1, self.mel_dim)    # un-group the r frames per decoder step
             post_in = states.reshape(batch, mel.size(1), -1) if self.use_decoder_state_for_postnet_input else mel
+            post_in = ops.grad_boundary(post_in, "postnet")     # its gradient ready <=> the postnet's backward is done
             linear = self.postnet(post_in, spk)
             assert linear.size(-1) == self.linear_dim
             return mel, linear, alignments, done

@@ -71,7 +71,7 @@ class WeightBank:
         self.active = False              # inside TrainStep._forward_backward
         self.fresh = False               # operand planes match the current parameter values
         self._fwd = None                 # (device table, n, norm_blocks, pack_blocks, layers)
-        self._bwd = None                 # (key, device table, n, blocks)
+        self._bwd = {}                   # pending-set key -> (device table, n, blocks); one entry per gradient bucket
 
     # -- forward ------------------------------------------------------------------------------------
     def begin_step(self):
@@ -134,7 +134,7 @@ class WeightBank:
             return
         key = tuple((L.v.data_ptr(), L.nsplit, L.partials.data_ptr(), L.v.grad.data_ptr(), L.g.grad.data_ptr())
                     for L in pend)
-        if self._bwd is None or self._bwd[0] != key:
+        if key not in self._bwd:
             if torch.cuda.is_current_stream_capturing():
                 raise Dv3Error("WeightBank: backward table changed during CUDA-graph capture (warm up first)")
             ents, blocks = [], 0
@@ -145,8 +145,8 @@ class WeightBank:
                 e.blk_bwd = blocks
                 blocks += L.Cout
                 ents.append(e)
-            self._bwd = (key, _upload(ents, pend[0].v.device), len(ents), blocks)
-        _, tab, n, blocks = self._bwd
+            self._bwd[key] = (_upload(ents, pend[0].v.device), len(ents), blocks)
+        tab, n, blocks = self._bwd[key]
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         lib.call("dv3_weightnorm_bwd_batched", ctypes.c_void_p(tab.data_ptr()), n, blocks, 1, st)
         for L in pend:

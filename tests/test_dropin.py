@@ -1,0 +1,76 @@
+"""The drop-in claim, exercised: the reference's OWN ``train.py`` (loaded unchanged from oracle/_ref through
+oracle/ref_harness.py, which only stands in for uninstalled CLI / logging / text packages) runs on top of
+``deepvoice3_pytorch_b200`` -- ``build_model()``, ``collate_fn`` and the ``train()`` loop with ``model(...)``,
+``loss.backward()``, ``clip_grad_norm_`` and ``torch.optim.Adam`` -- and produces the same losses as the same file on
+the reference package."""
+import numpy as np
+import pytest
+import torch
+
+
+def _harness():
+    from oracle import ref_harness as H
+    if H.ref_root() is None:
+        pytest.skip("oracle/_ref not built (python oracle/make_ref.py in the build container)")
+    return H
+
+
+def test_train_py_build_model_on_this_package_cpu():
+    """train.py:812-840 ``build_model()`` bound to this package: same class surface, same state_dict keys and -- for
+    the same seed -- bit-identical initial weights as on the reference package."""
+    H = _harness()
+    sds = {}
+    for which in ("reference", "b200"):
+        tr = H.load_train(which)
+        H.apply_preset(tr, "deepvoice3_ljspeech")
+        torch.manual_seed(0)
+        model = tr.build_model()
+        assert hasattr(model, "get_trainable_parameters") and hasattr(model.seq2seq.decoder, "max_decoder_steps")
+        sds[which] = model.state_dict()
+    assert type(model).__module__.startswith("deepvoice3_pytorch_b200")
+    assert list(sds["reference"].keys()) == list(sds["b200"].keys())
+    for k in sds["reference"]:
+        assert torch.equal(sds["reference"][k], sds["b200"][k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,n_speakers", [("deepvoice3_ljspeech", 1), ("nyanko_ljspeech", 1),
+                                               ("deepvoice3_vctk", 108)])
+def test_reference_train_loop_runs_unchanged_on_this_package(preset, n_speakers, tmp_path):
+    """4 optimizer steps of reference ``train()`` on synthetic utterances batched by reference ``collate_fn``: the
+    reference package in PyTorch eager on the same GPU (TF32 off) vs this package (default tensor-core mode, eager --
+    what a user gets by pointing ``train.py`` at this package).  dropout = 0 so the two are comparable."""
+    H = _harness()
+    from torch.utils.data import DataLoader
+    logs = {}
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for which in ("reference", "b200"):
+            tr = H.load_train(which)
+            hp = H.apply_preset(tr, preset, dropout=0.0, eval_interval=10 ** 9)
+            torch.manual_seed(0)
+            model = tr.build_model().to("cuda")
+            opt = torch.optim.Adam(model.get_trainable_parameters(), lr=hp.initial_learning_rate,
+                                   betas=(hp.adam_beta1, hp.adam_beta2), eps=hp.adam_eps,
+                                   weight_decay=hp.weight_decay, amsgrad=hp.amsgrad)
+            utts = H.synthetic_utterances(16, seed=3, n_speakers=n_speakers, min_text=40, max_text=100, min_frames=200,
+                                          max_frames=400)
+            loader = DataLoader(utts, batch_size=4, collate_fn=tr.collate_fn, shuffle=False)
+            writer = H.ScalarLog()
+            tr.global_step, tr.global_epoch = 0, 0
+            tr.train(torch.device("cuda"), model, loader, opt, writer, init_lr=hp.initial_learning_rate,
+                     checkpoint_dir=str(tmp_path), checkpoint_interval=10 ** 9, nepochs=1,
+                     clip_thresh=hp.clip_thresh)
+            logs[which] = writer.scalars
+            del model, opt
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    for tag in ("loss", "mel_l1_loss", "linear_l1_loss", "done_loss", "attn_loss", "gradient norm"):
+        ref = np.array([v for _, v in logs["reference"][tag]])
+        got = np.array([v for _, v in logs["b200"][tag]])
+        assert len(ref) == 4 and len(got) == 4, tag
+        np.testing.assert_allclose(got[0], ref[0], rtol=2e-4, err_msg=tag + " (first step: identical weights)")
+        np.testing.assert_allclose(got, ref, rtol=5e-3, err_msg=tag)
+    assert all(np.isfinite(v) for _, v in logs["b200"]["loss"])

@@ -84,13 +84,16 @@ def synthetic_batch(B, T_text, T_dec, n_speakers, seed, ragged=True):
     return text, mel, tpos, fpos, lengths, spk
 
 
-@pytest.mark.parametrize("preset,B,math", [("deepvoice3_ljspeech", 4, "fp32"), ("deepvoice3_ljspeech", 4, "tc"),
-                                           ("nyanko_ljspeech", 2, "tc"), ("deepvoice3_vctk", 3, "tc")])
-def test_preset_model_vs_oracle(preset, B, math, monkeypatch):
-    """Full-width preset model, T_text=128, T_mel=800 (T_dec=200): forward + every parameter gradient, in both
-    ConvBlock arithmetic modes (exact-fp32 CUDA cores / tcgen05 split-bf16)."""
-    from deepvoice3_pytorch_b200 import builder, ops
-    monkeypatch.setattr(ops, "conv_math", math)
+_ORACLE_CACHE = {}
+
+
+def _preset_case(preset, B):
+    """Model weights, batch and the CPU oracle's outputs / gradients (fp32 = parity target, fp64 = error yardstick),
+    computed once per preset and shared by the arithmetic modes."""
+    key = (preset, B)
+    if key in _ORACLE_CACHE:
+        return _ORACLE_CACHE[key]
+    from deepvoice3_pytorch_b200 import builder
     from oracle import dv3_oracle as O
     from oracle.specs import spec_from_builder
     bname, kw = preset_kwargs(preset)
@@ -105,9 +108,8 @@ def test_preset_model_vs_oracle(preset, B, math, monkeypatch):
             elif n.endswith("bias"):
                 p.add_(0.05 * torch.randn(p.shape, generator=gen))
     sd = {k: v.clone() for k, v in model.state_dict().items()}
-    text, mel, tpos, fpos, lengths, spk = synthetic_batch(B, 128, 200, kw["n_speakers"], 77)
-
-    # CPU oracle: fp32 (the reference's arithmetic) and fp64 (the error yardstick), all parameters as leaves
+    batch = synthetic_batch(B, 128, 200, kw["n_speakers"], 77)
+    text, mel, tpos, fpos, lengths, spk = batch
     spec = spec_from_builder(bname, **kw)
 
     def run_oracle(dtype):
@@ -117,35 +119,47 @@ def test_preset_model_vs_oracle(preset, B, math, monkeypatch):
         loss_o = sum((o * G.loss_weights(o.shape, i, dtype=dtype)).sum() / o.numel() ** 0.5
                      for i, o in enumerate(outs_o))
         loss_o.backward()
-        return outs_o, {k: v.grad for k, v in leaves.items() if torch.is_tensor(v) and v.grad is not None}
+        return [o.detach() for o in outs_o], {k: v.grad for k, v in leaves.items()
+                                              if torch.is_tensor(v) and v.grad is not None}
 
     outs_ref, grads32 = run_oracle(torch.float32)
     _, grads64 = run_oracle(torch.float64)
+    _ORACLE_CACHE[key] = (bname, kw, sd, batch, outs_ref, grads32, grads64)
+    return _ORACLE_CACHE[key]
 
+
+_FP32_MODE_ERR = {}        # (preset, parameter) -> relative L2 gradient error of the exact-fp32 mode (filled by the fp32 rows)
+
+
+@pytest.mark.parametrize("math", ["fp32", "tc"])          # fp32 rows first: the tc rows compare against their errors
+@pytest.mark.parametrize("preset", ["deepvoice3_ljspeech", "nyanko_ljspeech", "deepvoice3_vctk"])
+def test_preset_model_vs_oracle(preset, math, monkeypatch):
+    """The three BASELINE.json presets at the benchmark size -- B=16, T_text=128, T_mel=800 (T_dec=200) -- forward +
+    every parameter gradient, in both ConvBlock arithmetic modes (tcgen05 fp16/bf16 operand pairs = the benched mode;
+    exact-fp32 CUDA cores), at north_star's tolerance: rtol=1e-3 / atol=1e-4 on every output."""
+    from deepvoice3_pytorch_b200 import builder, ops
+    monkeypatch.setattr(ops, "conv_math", math)
+    B = 16
+    bname, kw, sd, (text, mel, tpos, fpos, lengths, spk), outs_ref, grads32, grads64 = _preset_case(preset, B)
+    model = getattr(builder, bname)(**kw)
+    model.load_state_dict(sd)
     model = model.cuda().train()
     outs = model(text.cuda(), mel.cuda(), speaker_ids=None if spk is None else spk.cuda(),
                  text_positions=tpos.cuda(), frame_positions=fpos.cuda(), input_lengths=lengths)
     names = ["mel", "linear", "alignments", "done"]
-    # Every block of the "tc" mode is within ~1e-5 of exact fp32 (tests/test_gpu_blocks.py holds it to rtol 1e-3 /
-    # atol 1e-4 per block); over the ~30 blocks of a preset model that accumulates to <= ~2e-4 absolute on the
-    # sigmoid outputs, so the FULL-DEPTH comparison of the tensor-core mode uses atol 4e-4 (the exact-fp32 mode
-    # keeps north_star's 1e-4).  tools/precision_report.py prints both modes against the fp64 oracle.
-    atol = 4e-4 if math == "tc" else 1e-4
     for i, (o, r) in enumerate(zip(outs, outs_ref)):
         assert o.shape == r.shape
-        close(o, r, rtol=1e-3, atol=atol, what="%s %s" % (preset, names[i]))
+        close(o, r, rtol=1e-3, atol=1e-4, what="%s %s (%s)" % (preset, names[i], math))
     loss = sum((o * G.loss_weights(o.shape, i, "cuda")).sum() / o.numel() ** 0.5 for i, o in enumerate(outs))
     loss.backward()
-    # Gradients here are sums of ~1e5-1e7 signed terms (the projection loss above cancels heavily), so two fp32
-    # implementations differ by their accumulated round-off -- the CPU fp32 restatement itself is only good to
-    # ~1e-3..6e-3 against fp64 on some tensors, and parameters with an exactly-zero true gradient (the key-projection
-    # bias: softmax is shift invariant) carry pure noise.  Yardstick: relative L2 error against the fp64 oracle must
-    # be <= 1e-3, or <= 8x the error the CPU fp32 restatement makes on the same tensor.  In the tensor-core mode the
-    # forward differs from exact fp32 by ~5e-6, enough to flip a handful of ReLU decisions at pre-activations within
-    # that distance of zero (1x1 conv + ReLU stacks); each flip moves a per-channel sum of ~1e3 terms by a whole term,
-    # i.e. ~1e-2 relative L2 on bias / weight gradients behind a ReLU -- inherent to comparing ReLU networks across
-    # roundings, so that mode's floor is 2e-2.
-    floor = 2e-2 if math == "tc" else 1e-3
+    # Gradients here are sums of ~1e5-1e7 signed terms (the projection loss above cancels heavily), so ANY two fp32
+    # implementations differ by their accumulated round-off: at B=16 the exact-fp32 CUDA-core mode itself reaches
+    # 2e-3..6e-3 relative L2 against fp64 on a few tensors (bias / weight_g gradients: atomics in a different order),
+    # and parameters with an exactly-zero true gradient (the key-projection bias: softmax is shift invariant) carry
+    # pure noise.  Two yardsticks:
+    #  (1) both modes: relative L2 error against the fp64 oracle <= 1e-2, or <= 8x the CPU fp32 oracle's own error;
+    #  (2) the tensor-core mode additionally must not be less accurate than the exact-fp32 mode: per tensor
+    #      err_tc <= max(1e-3, 3 * err_exact_fp32)  -- i.e. split fp16 / bf16 operand pairs cost no gradient accuracy.
     worst = 0.0
     for k, p in model.named_parameters():
         if k not in grads64:
@@ -158,5 +172,11 @@ def test_preset_model_vs_oracle(preset, B, math, monkeypatch):
         err = float((p.grad.cpu().double() - truth).norm()) / norm
         err32 = float((grads32[k].double() - truth).norm()) / norm
         worst = max(worst, err)
-        assert err < max(floor, 8 * err32), "%s: relative L2 gradient error %.3e (cpu fp32: %.3e)" % (k, err, err32)
-    print("worst relative L2 gradient error vs fp64: %.3e" % worst)
+        assert err < max(1e-2, 8 * err32), "%s (%s): relative L2 gradient error %.3e (cpu fp32: %.3e)" % (k, math, err,
+                                                                                                          err32)
+        if math == "fp32":
+            _FP32_MODE_ERR[(preset, k)] = err
+        elif (preset, k) in _FP32_MODE_ERR:
+            ref = _FP32_MODE_ERR[(preset, k)]
+            assert err < max(1e-3, 3 * ref), "%s: tensor-core mode %.3e vs exact-fp32 mode %.3e" % (k, err, ref)
+    print("worst relative L2 gradient error vs fp64 (%s, %s): %.3e" % (preset, math, worst))

@@ -225,3 +225,66 @@ def test_spec_loss_kernel_matches_reference_spec_loss(name):
     want = (1 - bw) * float(case["out"]["l1"]) + bw * float(case["out"]["bd"])
     np.testing.assert_allclose(float(loss), want, rtol=1e-5)
     np.testing.assert_allclose(grad[:, :T].cpu().numpy(), case["out"]["grad"], rtol=1e-3, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_dropout_masks_change_every_training_forward_without_trainstep():
+    """A plain model(...) / loss.backward() / optimizer.step() loop (reference train.py on this package) must see a
+    fresh dropout mask every step: the model's own forward draws a new seed (ops.DropoutState.begin_forward); eval
+    forwards are deterministic; the backward uses the mask of ITS forward even if another forward ran in between."""
+    from deepvoice3_pytorch_b200 import builder
+    kw = dict(n_vocab=149, embed_dim=64, mel_dim=80, linear_dim=129, r=1, downsample_step=4, kernel_size=3,
+              encoder_channels=128, decoder_channels=128, converter_channels=128, use_memory_mask=True,
+              key_projection=True, value_projection=True, dropout=0.2, max_positions=256)
+    torch.manual_seed(0)
+    model = builder.deepvoice3(**kw).cuda()
+    host = __import__("deepvoice3_pytorch_b200.train_step", fromlist=["x"]).make_synthetic_batch(
+        B=4, T_text=48, T_mel=512, linear_dim=129, seed=2)
+    b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in host.items()}
+
+    def fwd():
+        return model(b["x"], b["mel"], text_positions=b["text_positions"], frame_positions=b["frame_positions"],
+                     input_lengths=b["input_lengths"])
+    model.train()
+    o1 = fwd()
+    o2 = fwd()
+    assert not torch.equal(o1[1], o2[1]), "two training forwards used the same dropout masks"
+    # backward of the FIRST forward after a second forward ran: gradients must equal those of an isolated run
+    g_after = torch.autograd.grad(o1[1].sum(), model.postnet.convolutions[0].weight_v, retain_graph=False)[0]
+    assert torch.isfinite(g_after).all() and float(g_after.abs().max()) > 0
+    model.eval()
+    with torch.no_grad():
+        e1, e2 = fwd(), fwd()
+    assert torch.equal(e1[1], e2[1])
+    # model.postnet called on its own (reference train.py:700) also draws fresh masks
+    model.train()
+    x = torch.rand(4, 128, 128, device="cuda")
+    assert not torch.equal(model.postnet(x), model.postnet(x))
+
+
+@pytest.mark.gpu
+def test_train_step_checkpoint_resume():
+    """TrainStep.state_dict() -> a new TrainStep.load_state_dict() continues exactly: Adam moments, bias-correction
+    step and the learning-rate schedule position are restored (reference checkpoint keys, train.py:787-810)."""
+    from deepvoice3_pytorch_b200 import builder, ops
+    from deepvoice3_pytorch_b200.train_step import TrainStep, make_synthetic_batch, to_device
+    kw = dict(n_vocab=149, embed_dim=64, mel_dim=80, linear_dim=129, r=1, downsample_step=4, kernel_size=3,
+              encoder_channels=128, decoder_channels=128, converter_channels=128, use_memory_mask=True,
+              key_projection=True, value_projection=True, dropout=0.0, max_positions=256)
+    dev = to_device(make_synthetic_batch(B=2, T_text=24, T_mel=64, linear_dim=129, seed=9), "cuda")
+    torch.manual_seed(0)
+    a = TrainStep(builder.deepvoice3(**kw).cuda().train())
+    for _ in range(3):
+        a.step(dev)
+    ckpt = a.state_dict(global_epoch=7)
+    assert set(ckpt) == {"state_dict", "optimizer", "global_step", "global_epoch"} and ckpt["global_step"] == 3
+    ckpt = {k: (v if not isinstance(v, dict) else __import__("copy").deepcopy(v)) for k, v in ckpt.items()}
+    want = [float(a.step(dev)) for _ in range(2)]
+    torch.manual_seed(123)                                   # different init: everything must come from the checkpoint
+    b = TrainStep(builder.deepvoice3(**kw).cuda().train())
+    assert b.load_state_dict(ckpt) == 7 and b.global_step == 3 and b.opt.t == 3
+    got = [float(b.step(dev)) for _ in range(2)]
+    np.testing.assert_allclose(got, want, rtol=1e-5)
+    # ... and torch.optim.Adam accepts the optimizer part (a reference-side load_checkpoint)
+    opt = torch.optim.Adam(b.model.get_trainable_parameters(), lr=1.0)
+    opt.load_state_dict(b.opt.state_dict())
