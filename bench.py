@@ -57,7 +57,8 @@ PRESETS = {
 B, T_TEXT, T_MEL = 16, 128, 800
 METRIC = "mel-frames/sec training step (B=16,T_mel=800)"
 WORKLOAD = "%s training step, B=16/GPU, T_text=128, T_mel=800 (T_dec=200)"
-NCU_TRAFFIC_GATED_512_800 = None      # filled from profiles/r02_ncu_full_tc_conv.csv once captured
+NCU_TRAFFIC_GATED_512_800 = 90.40e6   # dram__bytes_read.sum + dram__bytes_write.sum (58.82 + 31.58 MB) of the (16,512,800)
+                                      # gated forward, profiles/r02_ncu_full_conv.csv (`ncu --set full` of this kernel)
 
 
 def peaks():
@@ -366,11 +367,11 @@ def convblock_roofline(dev, pk, pk_kind):
                   "of the step: 50 launches, time-weighted) via dv3_tc_convblock_fwd / dv3_tc_conv",
         "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
         "issued_tflops": 3 * ach, "issued_frac": 3 * ach / pk["bf16_tflops"],
-        "note": "achieved counts ALGORITHMIC flops (one fp32 multiply-add per term); the kernels issue 3 16-bit MMA "
-                "passes per term (hi*hi, hi*lo, lo*hi of fp16 / bf16 operand pairs) for fp32-class results",
+        "note": "achieved counts ALGORITHMIC flops (one fp32 multiply-add per term); the kernels issue 3 fp16 MMA "
+                "passes per term (hi*hi, hi*lo, lo*hi of fp16 operand pairs) for fp32-class results",
         "family_us_per_step": tot_t * 1e6, "shapes": rows, "peak_source": pk_kind,
         # dram__bytes_read.sum + dram__bytes_write.sum of the (16,512,800) gated forward from the committed
-        # `ncu --set full` capture of THIS kernel (profiles/r02_ncu_full_tc_conv.csv); null until captured
+        # `ncu --set full` capture of THIS kernel (profiles/r02_ncu_full_conv.csv)
         "traffic": NCU_TRAFFIC_GATED_512_800,
         "largest_member": {"shape": "(B=16,C=512,T=800,k=3) gated forward", "launch_us": tf * 1e6,
                            "achieved": flops / tf / 1e12, "frac": flops / tf / 1e12 / pk["bf16_tflops"],
@@ -487,16 +488,16 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": frames * args.steps / t_res, "unit": "mel-frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_res / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"tc": "fp16-pair (forward) / bf16-pair (gradients) tensor-core products -> f32", "bf16x3": "as tc",
-                  "fp32": "f32"}[args.math], "data": "synthetic",
+        "dtype": {"tc": "f32 via split-fp16 pairs (3 fp16 tcgen05 MMA passes per product, fp32 accumulate)",
+                  "bf16x3": "as tc", "fp32": "f32"}[args.math], "data": "synthetic",
         "config": {"workload": WORKLOAD % args.preset + ", random-init weights, fwd+losses+bwd+clip+Adam",
                    "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "inputs larger than L2 (>1.5 GB touched per step)",
                    "cuda_graph": not args.no_graph, "conv_math": args.math,
-                   "conv_math_note": {"tc": "tcgen05: every fp32 operand as a 16-bit (hi, lo) pair, hi*hi + hi*lo + lo*hi "
-                                            "with fp32 accumulation; fp16 pairs (22-bit operands) in the forward, bf16 "
-                                            "pairs in the gradient GEMMs; full-depth preset models within rtol 1e-3 / atol "
-                                            "1e-4 of the fp32 oracle at B=16 (tests/test_gpu_models.py)",
+                   "conv_math_note": {"tc": "tcgen05: every fp32 operand as an fp16 (hi, lo*2^11) pair = 22-bit operands, "
+                                            "hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (gradient operands "
+                                            "pre-scaled by 2^10); all three presets within rtol 1e-3 / atol 1e-4 of the "
+                                            "fp32 oracle at B=16, full depth (tests/test_gpu_models.py)",
                                       "bf16x3": "alias of tc",
                                       "fp32": "exact fp32 FMA on CUDA cores"}[args.math]},
         "e2e": {"value": frames * args.steps / t_e2e, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d,

@@ -3,7 +3,8 @@
 GPU pass (csrc/stft.cu) instead of two CPU lws STFTs.  ``stft_mel_batch`` is the batched device API the
 preprocessors should use (a whole shard of clips per launch; one H2D, one D2H).
 
-Out of scope (reference audio.py:37-43): ``inv_spectrogram`` / LWS phase recovery -- inference-only vocoding.
+``inv_spectrogram`` (reference audio.py:37-43) is provided with Griffin-Lim phase recovery on the same STFT frame: the
+reference's LWS (``lws`` package) is an un-vendored dependency, so that path's parity is unpinned (csrc/istft.cu).
 """
 import ctypes
 
@@ -24,6 +25,8 @@ class _HP:
     preemphasis = 0.97
     min_level_db = -100
     ref_level_db = 20
+    power = 1.4                   # spectrogram sharpening before phase recovery (presets/*.json)
+    griffin_lim_iters = 60
 
 
 hparams = _HP()
@@ -137,3 +140,57 @@ def _normalize(S):
 
 def _denormalize(S):
     return (np.clip(S, 0, 1) * -hparams.min_level_db) + hparams.min_level_db
+
+
+def _cp(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def inv_num_samples(n_frames):
+    """Samples reconstructed from n_frames frames (the hop-aligned length whose forward STFT has n_frames frames)."""
+    return (int(n_frames) - 1) * hparams.hop_size - (hparams.fft_size - 2 * hparams.hop_size)
+
+
+def griffin_lim(mag, n_iter=None):
+    """mag: (T, 513) fp32 CUDA tensor of linear magnitudes -> waveform (n,) whose STFT magnitude approximates it.
+    x <- istft(mag * exp(i*angle(stft(x)))), started from the zero-phase inverse; every arrow is one kernel launch."""
+    if not (torch.is_tensor(mag) and mag.is_cuda and mag.dtype == torch.float32 and mag.dim() == 2):
+        raise Dv3Error("griffin_lim needs a (T, 513) fp32 CUDA tensor; there is no CPU path")
+    if hparams.fft_size != 1024 or hparams.hop_size != 256 or mag.shape[1] != 513:
+        raise Dv3Error("the inverse kernels are built for fft_size=1024, hop_size=256")
+    mag = mag.contiguous()
+    T = mag.shape[0]
+    n = inv_num_samples(T)
+    if n < 1:
+        raise Dv3Error("too few frames (%d) to reconstruct a waveform" % T)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    spec = torch.zeros(T, 513, 2, device=mag.device)
+    spec[..., 0] = mag                                   # zero phase
+    x = torch.zeros(n, device=mag.device)
+    lib.call("dv3_istft", _cp(spec), _cp(x), n, T, st)
+    for _ in range(hparams.griffin_lim_iters if n_iter is None else n_iter):
+        lib.call("dv3_stft_complex", _cp(x), n, _cp(mag), _cp(spec), T, st)
+        x.zero_()
+        lib.call("dv3_istft", _cp(spec), _cp(x), n, T, st)
+    return x
+
+
+def inv_preemphasis(x):
+    """y[n] = x[n] + c*y[n-1] -- reference audio.py:26-28.  x: (n,) or (nclips, n) fp32 CUDA tensor."""
+    x2 = x.view(1, -1) if x.dim() == 1 else x
+    x2 = x2.contiguous()
+    y = torch.empty_like(x2)
+    lib.call("dv3_deemphasis", _cp(x2), _cp(y), x2.shape[0], x2.shape[1], x2.shape[1], float(hparams.preemphasis),
+             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    return y.view_as(x)
+
+
+def inv_spectrogram(spectrogram, n_iter=None):
+    """(513, T) normalised dB spectrogram (what ``spectrogram`` returns / the model predicts, transposed) -> waveform
+    float32 numpy array -- reference audio.py:37-43: denormalise, dB -> amplitude, ** power, phase recovery, inverse
+    STFT, de-emphasis."""
+    S = torch.as_tensor(np.ascontiguousarray(np.asarray(spectrogram, dtype=np.float32).T)).cuda()   # (T, 513)
+    amp = torch.empty_like(S)
+    lib.call("dv3_spec_to_amp", _cp(S), _cp(amp), S.numel(), float(hparams.min_level_db), float(hparams.ref_level_db),
+             float(hparams.power), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    return inv_preemphasis(griffin_lim(amp, n_iter)).cpu().numpy()

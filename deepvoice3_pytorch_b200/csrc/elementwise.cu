@@ -73,25 +73,53 @@ __global__ void sinusoid_fwd_kernel(const long long* __restrict__ pos, const flo
 // dtable[pos,i] += dy * d/da * w ; dw[b] += sum dy * d/da * table   (row 0 / padding gets nothing)
 __global__ void sinusoid_bwd_kernel(const long long* __restrict__ pos, const float* __restrict__ table,
                                     const float* __restrict__ w, int nw, const float* __restrict__ dy,
-                                    float* __restrict__ dtable, float* __restrict__ dw, int B, int T, int D,
-                                    int P) {
+                                    float* __restrict__ dtable, int B, int T, int D, int P) {
     pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (n >= B * T) return;
     const long long ps = pos[n];
     if (ps <= 0 || ps >= P) return;
-    const int wi = nw == 1 ? 0 : n / T;
-    const float wb = w[wi];
+    const float wb = w[nw == 1 ? 0 : n / T];
     const float* row = table + (size_t)ps * D;
-    float acc = 0.f;
     for (int i = lane; i < D; i += 32) {
-        const float tv = row[i], a = wb * tv;
+        const float a = wb * row[i];
         const float da = dy[(size_t)n * D + i] * ((i & 1) ? -sinf(a) : cosf(a));
-        if (dtable) atomicAdd(&dtable[(size_t)ps * D + i], da * wb);
-        acc = fmaf(da, tv, acc);
+        atomicAdd(&dtable[(size_t)ps * D + i], da * wb);
     }
-    acc = warp_sum(acc);
-    if (lane == 0 && dw) atomicAdd(&dw[wi], acc);
+}
+
+// d(loss)/d(position rate): dw[wi] = sum over the rows of utterance wi (all rows if nw == 1) of <dy * d(enc)/d(a), table>.
+// The sum cancels heavily (its terms are O(1), the result often 1e-4 of that), so it is accumulated in double by ONE
+// CTA per rate, in a fixed order: deterministic, and as accurate as the fp32 CPU reference (float atomics over the
+// rows gave 4e-2 relative error on the multi-speaker position-rate projections).
+__global__ void __launch_bounds__(256) sinusoid_dw_kernel(const long long* __restrict__ pos,
+                                                          const float* __restrict__ table,
+                                                          const float* __restrict__ w, int nw,
+                                                          const float* __restrict__ dy, float* __restrict__ dw, int B,
+                                                          int T, int D, int P) {
+    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
+    __shared__ double red[8];
+    const int wi = blockIdx.x;
+    const int r0 = nw == 1 ? 0 : wi * T, r1 = nw == 1 ? B * T : (wi + 1) * T;
+    const float wb = w[wi];
+    double acc = 0.0;
+    const long long total = (long long)(r1 - r0) * D;
+    for (long long q = threadIdx.x; q < total; q += blockDim.x) {
+        const int n = r0 + (int)(q / D), i = (int)(q % D);
+        const long long ps = pos[n];
+        if (ps <= 0 || ps >= P) continue;
+        const float tv = table[(size_t)ps * D + i], a = wb * tv;
+        acc += (double)(dy[(size_t)n * D + i] * ((i & 1) ? -sinf(a) : cosf(a))) * (double)tv;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        dw[wi] += (float)t;
+    }
 }
 
 // ---- standalone dropout (inputs / embeddings / speaker embeddings): reference F.dropout call sites
@@ -223,9 +251,16 @@ int dv3_sinusoid_fwd(const long long* pos, const float* table, const float* w, i
 }
 int dv3_sinusoid_bwd(const long long* pos, const float* table, const float* w, int nw, const float* dy,
                      float* dtable, float* dw, int B, int T, int D, int P, void* stream) {
-    launch_k(sinusoid_bwd_kernel, ceil_div(B * T * 32, 256), 256, 0, (cudaStream_t)stream, pos, table, w, nw, dy,
-                                                                                    dtable, dw, B, T, D, P);
-    return check_launch("sinusoid_bwd");
+    if (dtable) {
+        launch_k(sinusoid_bwd_kernel, ceil_div(B * T * 32, 256), 256, 0, (cudaStream_t)stream, pos, table, w, nw, dy,
+                 dtable, B, T, D, P);
+        if (int e = check_launch("sinusoid_bwd(table)")) return e;
+    }
+    if (dw) {
+        launch_k(sinusoid_dw_kernel, nw, 256, 0, (cudaStream_t)stream, pos, table, w, nw, dy, dw, B, T, D, P);
+        if (int e = check_launch("sinusoid_bwd(rate)")) return e;
+    }
+    return 0;
 }
 
 int dv3_dropout(const float* x, float* y, long long n, float p, const unsigned long long* seed_ptr, unsigned salt,

@@ -10,12 +10,10 @@
 
 namespace dv3 {
 
-// x (B,C,T) fp32 -> conv-input dropout -> (hi, lo) fp16 planes in (B,T,Cp) [forward operand] and, when wg != NULL, the
-// same values as a bf16 pair [operand of the weight gradient, which multiplies them with bf16 gradient planes:
-// tcgen05 kind::f16 cannot mix fp16 and bf16 operands].  32(c) x 32(t) tile per CTA, block (32, 8).
-__global__ void split_input_kernel(const float* __restrict__ x, bf16* __restrict__ btc, bf16* __restrict__ wg, int Bn,
-                                   int C, int Cp, int T, float p, const unsigned long long* __restrict__ seed_ptr,
-                                   unsigned salt) {
+// x (B,C,T) fp32 -> conv-input dropout -> (hi, lo) fp16 planes in (B,T,Cp): the forward GEMM's K-major operand and
+// the weight gradient's MN-major operand.  32(c) x 32(t) tile per CTA, block (32, 8).
+__global__ void split_input_kernel(const float* __restrict__ x, bf16* __restrict__ btc, int Bn, int C, int Cp, int T,
+                                   float p, const unsigned long long* __restrict__ seed_ptr, unsigned salt) {
     pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
     __shared__ float tile[32][33];
     const DropCfg drop = make_drop(p, seed_ptr, salt);
@@ -35,15 +33,12 @@ __global__ void split_input_kernel(const float* __restrict__ x, bf16* __restrict
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
-        if (c < C && t < T) {
-            const float v = tile[threadIdx.x][threadIdx.y + 8 * i];
-            split_store<FMT_F16>(v, btc, ((size_t)b * T + t) * Cp + c, btc_plane);
-            if (wg) split_store<FMT_BF16>(v, wg, ((size_t)b * T + t) * Cp + c, btc_plane);
-        }
+        if (c < C && t < T)
+            split_store<FMT_F16>(tile[threadIdx.x][threadIdx.y + 8 * i], btc, ((size_t)b * T + t) * Cp + c, btc_plane);
     }
 }
 
-// gate backward (see conv.cu gate_bwd_kernel) producing dAB = [da ; db] directly as 2 bf16 planes in
+// gate backward (see conv.cu gate_bwd_kernel) producing dAB = [da ; db] * GRAD_SCALE directly as 2 fp16 planes in
 // (B,T,2C) [data-gradient operand] and (B,2C,T) [weight-gradient operand]; dbias[2C] += sums over (b,t).
 __global__ void gate_bwd_split_kernel(const float* __restrict__ dy, const float* __restrict__ a,
                                       const float* __restrict__ s, const float* __restrict__ x,
@@ -76,8 +71,8 @@ __global__ void gate_bwd_split_kernel(const float* __restrict__ dy, const float*
         const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
         if (c < C && t < T) {
             const size_t o = ((size_t)b * T + t) * 2 * C + c;
-            split_store<FMT_BF16>(ta[threadIdx.x][threadIdx.y + 8 * i], btc, o, plane);
-            split_store<FMT_BF16>(tb[threadIdx.x][threadIdx.y + 8 * i], btc, o + C, plane);
+            split_store<FMT_F16>(ta[threadIdx.x][threadIdx.y + 8 * i] * GRAD_SCALE, btc, o, plane);
+            split_store<FMT_F16>(tb[threadIdx.x][threadIdx.y + 8 * i] * GRAD_SCALE, btc, o + C, plane);
         }
     }
 }
@@ -107,8 +102,8 @@ __global__ void grad_split_kernel(const float* __restrict__ dy, const float* __r
         for (int i = 0; i < 4; ++i) {
             const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
             if (c < C && t < T)
-                split_store<FMT_BF16>(tile[threadIdx.x][threadIdx.y + 8 * i], btc, ((size_t)b * T + t) * Cp + c,
-                                      (size_t)Bn * T * Cp);
+                split_store<FMT_F16>(tile[threadIdx.x][threadIdx.y + 8 * i] * GRAD_SCALE, btc,
+                                     ((size_t)b * T + t) * Cp + c, (size_t)Bn * T * Cp);
         }
     }
 }
@@ -142,12 +137,12 @@ extern "C" {
 int dv3_tc_split_input(const float* x, void* btc, int npl, void* bct, int B, int C, int T, int k, int dilation,
                        int causal, float p_drop, const unsigned long long* seed_ptr, unsigned salt, void* stream) {
     DV3_REQUIRE(B <= 65535 && (C + 31) / 32 <= 65535, "tc_split_input: grid too large");
-    DV3_REQUIRE(npl == 2, "tc_split_input: npl must be 2");
+    DV3_REQUIRE(npl == 2 && bct == nullptr, "tc_split_input: npl must be 2 and bct NULL (the weight gradient reads btc)");
     (void)k; (void)dilation; (void)causal;
     const int Cp = (C + 7) / 8 * 8;
     dim3 grid((T + 31) / 32, (C + 31) / 32, B);
-    launch_k(split_input_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, x, (bf16*)btc, (bf16*)bct, B, C, Cp, T, p_drop,
-             seed_ptr, salt);
+    launch_k(split_input_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, x, (bf16*)btc, B, C, Cp, T, p_drop, seed_ptr,
+             salt);
     return check_launch("tc_split_input");
 }
 
@@ -171,7 +166,7 @@ int dv3_tc_grad_split(const float* dy, const float* y, void* btc, void* bct, flo
 
 // Weight norm + split for a conv weight v (Cout, Cin, k), g [Cout]:
 //   wfwd: [2][k][Cout][Cinp] fp16 planes (forward operand: rows co, K = ci)
-//   wbwd: [2][k][Cin][Coutp] bf16 planes (data-gradient operand, multiplied with bf16 gradient planes)
+//   wbwd: [2][k][Cin][Coutp] fp16 planes (data-gradient operand)
 int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wfwd, int npl,
                           void* wbwd, int Cout, int Cin, int k, void* stream) {
     DV3_REQUIRE(npl == 2, "tc_weightnorm_fwd: npl must be 2");
@@ -181,7 +176,7 @@ int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float
     launch_k(wn_norm_kernel2, (Cout * 32 + 255) / 256, 256, 0, st, v, g, inv_norm, scale, Cout, L);
     if (int e = check_launch("tc_weightnorm_fwd(norm)")) return e;
     dim3 grid((L + 31) / 32, (Cout + 31) / 32);
-    launch_k(wn_pack_split_kernel<FMT_F16, FMT_BF16>, grid, dim3(32, 8), 0, st, v, scale, (bf16*)wfwd, Cinp, 1,
+    launch_k(wn_pack_split_kernel<FMT_F16, FMT_F16>, grid, dim3(32, 8), 0, st, v, scale, (bf16*)wfwd, Cinp, 1,
              (long long)Cout * Cinp, (long long)k * Cout * Cinp, (bf16*)wbwd, 1, Coutp, (long long)Cin * Coutp,
              (long long)k * Cin * Coutp, Cout, Cin, k);
     return check_launch("tc_weightnorm_fwd(pack)");
@@ -189,7 +184,7 @@ int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float
 
 // ConvTranspose1d(k=2,s=2) weight v (Cin, Cout, 2), g [Cin] (norm over dim 0 = Cin), run as a 1x1 conv with
 // 2*Cout output rows ordered (j, co):
-//   wfwd: [2][2*Cout][Cinp] fp16, rows (j,co), K = ci        wbwd: [2][Cin][K2p] bf16, rows ci, K = (j,co)
+//   wfwd: [2][2*Cout][Cinp] fp16, rows (j,co), K = ci        wbwd: [2][Cin][K2p] fp16, rows ci, K = (j,co)
 int dv3_tc_weightnorm_convt_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wfwd, int npl,
                                 void* wbwd, int Cin, int Cout, void* stream) {
     DV3_REQUIRE(npl == 2, "tc_weightnorm_convt_fwd: npl must be 2");
@@ -200,7 +195,7 @@ int dv3_tc_weightnorm_convt_fwd(const float* v, const float* g, float* inv_norm,
     if (int e = check_launch("tc_weightnorm_convt_fwd(norm)")) return e;
     dim3 grid((L + 31) / 32, (Cin + 31) / 32);
     // r = ci, x = co, j: outA (lanes along (x,j)) = wbwd [ci][j*Cout+co] ; outB (lanes along r) = wfwd [(j*Cout+co)][ci]
-    launch_k(wn_pack_split_kernel<FMT_BF16, FMT_F16>, grid, dim3(32, 8), 0, st, v, scale, (bf16*)wbwd, K2p, 1,
+    launch_k(wn_pack_split_kernel<FMT_F16, FMT_F16>, grid, dim3(32, 8), 0, st, v, scale, (bf16*)wbwd, K2p, 1,
              (long long)Cout, (long long)Cin * K2p, (bf16*)wfwd, 1, Cinp, (long long)Cout * Cinp,
              (long long)2 * Cout * Cinp, Cin, Cout, 2);
     return check_launch("tc_weightnorm_convt_fwd(pack)");

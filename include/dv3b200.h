@@ -158,6 +158,19 @@ int dv3_stft_mel(const float* wav, const int* lengths, const float* mel_basis, c
                  const int* mel_len, float* linear, float* mel, int nclips, int max_len, int max_frames,
                  int n_mels, float preemph, float min_level_db, float ref_level_db, void* stream);
 
+/* ---- inverse audio path: reference audio.py:37-43 (inv_spectrogram) and :26-28 (inv_preemphasis).  The reference
+ * recovers the phase with the un-vendored `lws` package (parity UNPINNED); restated here as Griffin-Lim on the same
+ * sqrt-Hann 1024 / hop 256 / 768-pad frame as dv3_stft_mel (sum of squared windows == 1: synthesis window = analysis
+ * window).  The iteration x <- istft(mag * exp(i angle(stft(x)))) is driven by the host (audio.inv_spectrogram).
+ * dv3_spec_to_amp: normalised dB (n) -> (10^((S*(-min)+min+ref)/20))^power.  dv3_stft_complex: wav (n_samples) ->
+ * spec (nframes,513,2) [re,im]; mag (nframes,513) != NULL projects the result onto that magnitude.  dv3_istft: spec ->
+ * wav (n_samples) += overlap-added frames (zero wav first).  dv3_deemphasis: y[n] = x[n] + coef*y[n-1] per clip. */
+int dv3_spec_to_amp(const float* spec_norm, float* amp, long long n, float min_level_db, float ref_level_db,
+                    float power, void* stream);
+int dv3_stft_complex(const float* wav, int n_samples, const float* mag, float* spec, int nframes, void* stream);
+int dv3_istft(const float* spec, float* wav, int n_samples, int nframes, void* stream);
+int dv3_deemphasis(const float* x, float* y, int nclips, int n_samples, long long stride, float coef, void* stream);
+
 /* ================= tensor-core ConvBlock / conv path: tcgen05 + TMA, split-bf16 operands =================
  * Same reference code as dv3_convblock_fwd / dv3_conv1d_fwd / dv3_conv1d_dgrad / dv3_conv1d_wgrad (modules.py:94-100,
  * 145-164, 200-226 and their autograd).  fp32 operands are split into bf16 planes p0 = bf16(x), p1 = bf16(x-p0)
@@ -166,11 +179,12 @@ int dv3_stft_mel(const float* wav, const int* lengths, const float* mel_basis, c
  * pitches are padded to a multiple of 8.  Callers use the exact-fp32 entry points for unsupported shapes. */
 int dv3_tc_supported(int B, int C, int T, int k);           /* gated block: C % 128 == 0, k <= 8 */
 int dv3_tc_conv_supported(int B, int Cin, int Cout, int T, int k);   /* plain conv: k == 1 or Cout % 128 == 0 */
-/* Operand planes: every fp32 operand x travels as hi = rn16(x), lo = rn16((x - hi) * 2^11) (csrc/common.cuh).
- * Forward GEMMs multiply fp16 pairs (22-bit operands: fp32-class results); gradient GEMMs multiply bf16 pairs (the
- * gradients need the fp32 exponent range) -- tcgen05 kind::f16 does not mix formats, so a conv input is split twice.
- * x (B,C,T) fp32 -> conv-input dropout -> btc: [2][B][T][Cp] fp16 pair (forward operand, Cp = pad8(C)) and
- * bct (may be NULL): [2][B][T][Cp] bf16 pair of the same values (operand of the weight gradient). npl must be 2. */
+/* Operand planes: every fp32 operand x travels as an fp16 pair hi = rn16(x), lo = rn16((x - hi) * 2^11)
+ * (csrc/common.cuh): 22-bit operands, fp32-class products.  Gradient planes (dv3_tc_gate_bwd_split, dv3_tc_grad_split,
+ * Dv3TcFuse.post_planes) hold the gradient times 2^10 so that 1e-9 .. 1e-2 magnitudes sit in the fp16 range; the
+ * data-gradient / weight-gradient epilogues multiply by 2^-10.
+ * x (B,C,T) fp32 -> conv-input dropout -> btc: [2][B][T][Cp] (Cp = pad8(C)): operand of the forward GEMM and of the
+ * weight gradient.  npl must be 2, bct NULL. */
 int dv3_tc_split_input(const float* x, void* btc, int npl, void* bct, int B, int C, int T, int k, int dilation,
                        int causal, float p_drop, const unsigned long long* seed_ptr, unsigned salt, void* stream);
 /* gate backward writing dAB = [da ; db] as planes btc: [2][B][T][2C] (dgrad operand), bct: [2][B][2C][T] (wgrad). */
@@ -206,8 +220,7 @@ int dv3_weightnorm_bwd_batched(const Dv3WnEntry* table_dev, int n, int bwd_block
 /* Work the GEMM epilogues can fuse for the neighbouring ops (NULL = none):
  *  - forward (dv3_tc_convblock_fwd, dv3_tc_conv): np != NULL -> also write the operand planes [2][B][T][np_pitch] of
  *    out * dropmask(np_p, np_seed, np_salt), i.e. what dv3_tc_split_input would produce for the CONSUMER conv
- *    (np_pitch = pad8(channels of this call's output)): np = the fp16 pair its forward GEMM reads, np_wg = the bf16
- *    pair its weight gradient reads (NULL when the consumer needs no weight gradient);
+ *    (np_pitch = pad8(channels of this call's output));
  *  - data gradient (dv3_tc_conv with transpose_taps = 1): post_kind != 0 -> the tensor this call writes is
  *    dL/d(output of a producer op); apply that producer's backward and emit ITS gradient planes + bias-gradient sums:
  *      1 GLU gate, 2 highway gate: post_a / post_s = the producer's saved a, s (post_x = its input, highway only),
@@ -215,7 +228,7 @@ int dv3_weightnorm_bwd_batched(const Dv3WnEntry* table_dev, int n, int bwd_block
  *      3 ReLU (post_a = the producer's output), 4 identity: planes [2][B][T][pad8(Nc)], post_dbias[Nc] += sums
  *    (what dv3_tc_gate_bwd_split / dv3_tc_grad_split would produce from this call's output). */
 typedef struct Dv3TcFuse {
-    void* np; void* np_wg; const unsigned long long* np_seed; float np_p; unsigned np_salt; int np_pitch;
+    void* np; const unsigned long long* np_seed; float np_p; unsigned np_salt; int np_pitch;
     int post_kind, post_residual;
     const float* post_a; const float* post_s; const float* post_x;
     void* post_planes; float* post_dbias;

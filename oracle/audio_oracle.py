@@ -124,3 +124,46 @@ def synthetic_clip(seed, n=220500, sr=22050):
         x += a * np.sin(2 * np.pi * (f0 * t + 0.5 * (f1 - f0) * t * t / t[-1]))
     env = 0.5 * (1 + np.sin(2 * np.pi * 0.7 * t + rng.uniform(0, 6.28)))
     return np.clip(x * env, -1, 1).astype(np.float32)
+
+
+# ---- inverse path (reference audio.py:37-43, :26-28).  PARITY UNPINNED: the reference's phase recovery is lws.run_lws
+# (source absent); this is the Griffin-Lim iteration the CUDA path implements, restated with numpy rfft / irfft.
+def lws_istft(spec, fsize=1024, fshift=256):
+    """(n_frames, fsize/2+1) complex -> waveform of (n_frames-1)*fshift - (fsize - 2*fshift) samples (synthesis window
+    = analysis window: their squares sum to 1 over the overlapping frames)."""
+    M = spec.shape[0]
+    pad = fsize - fshift
+    frames = np.fft.irfft(spec, n=fsize, axis=1) * lws_window(fsize, fshift)[None, :]
+    y = np.zeros((M - 1) * fshift + fsize)
+    for m in range(M):
+        y[m * fshift:m * fshift + fsize] += frames[m]
+    n = (M - 1) * fshift - (fsize - 2 * fshift)
+    return y[pad:pad + n]
+
+
+def griffin_lim(mag, n_iter=60):
+    mag = np.asarray(mag, dtype=np.float64)
+    x = lws_istft(mag.astype(np.complex128))
+    for _ in range(n_iter):
+        X = lws_stft(x)[:mag.shape[0]]
+        a = np.abs(X)
+        X = np.where(a > 0, mag * X / np.maximum(a, 1e-300), mag)
+        x = lws_istft(X)
+    return x
+
+
+def inv_preemphasis(x, coef=0.97):
+    """scipy.signal.lfilter([1], [1, -coef], x): y[n] = x[n] + coef*y[n-1]."""
+    y = np.empty(len(x), dtype=np.float64)
+    prev = 0.0
+    for i, v in enumerate(np.asarray(x, dtype=np.float64)):
+        prev = v + coef * prev
+        y[i] = prev
+    return y
+
+
+def inv_spectrogram(spectrogram, power=1.4, n_iter=60):
+    """(513, T) normalised dB -> waveform (reference audio.py:37-43 with Griffin-Lim in place of lws.run_lws)."""
+    S = np.clip(np.asarray(spectrogram, dtype=np.float64), 0, 1) * -HP["min_level_db"] + HP["min_level_db"]
+    amp = np.power(10.0, (S + HP["ref_level_db"]) * 0.05)
+    return inv_preemphasis(griffin_lim(amp.T ** power, n_iter), HP["preemphasis"])

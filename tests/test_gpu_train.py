@@ -258,7 +258,7 @@ def test_dropout_masks_change_every_training_forward_without_trainstep():
     assert torch.equal(e1[1], e2[1])
     # model.postnet called on its own (reference train.py:700) also draws fresh masks
     model.train()
-    x = torch.rand(4, 128, 128, device="cuda")
+    x = torch.rand(4, 128, model.postnet.in_dim, device="cuda")
     assert not torch.equal(model.postnet(x), model.postnet(x))
 
 
