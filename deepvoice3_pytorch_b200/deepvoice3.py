@@ -67,10 +67,14 @@ class Encoder(nn.Module):
                              dropout=dropout))
         self.convolutions = nn.ModuleList(layers)
 
-    def grad_bucket_split(self):
-        """Index into ``convolutions``: the layers from here on form the "encoder_hi" gradient bucket of the
-        data-parallel step (their backward finishes first; the encoder holds 60 % of the parameters)."""
-        return len(self.convolutions) * 2 // 5
+    def grad_bucket_splits(self):
+        """[(tag, index into ``convolutions``)]: layers [index, next index) form one gradient bucket of the
+        data-parallel step.  The encoder holds 60 % of the parameters and its backward runs last, from the last layer
+        down: "encoder_hi" is final (and its all-reduce starts) two thirds into the encoder's backward, "encoder_mid"
+        shortly before its end; only the first layers are left for the exposed bucket."""
+        n = len(self.convolutions)
+        hi, mid = n * 3 // 5, n // 4
+        return [("encoder_hi", hi), ("encoder_mid", mid)] if 0 < mid < hi < n else []
 
     def forward(self, text_sequences, text_positions=None, lengths=None, speaker_embed=None):
         """-> keys, values, both (B, T_text, embed_dim) (reference deepvoice3.py:69-105)."""
@@ -83,7 +87,7 @@ class Encoder(nn.Module):
             x = x + F.softsign(self.speaker_fc1(speaker_embed_btc))
         input_embedding = x
         x = run_conv_stack(self.convolutions, ops.transpose12(x), speaker_embed_btc,
-                           boundaries={self.grad_bucket_split(): "encoder_hi"})
+                           boundaries={i: tag for tag, i in self.grad_bucket_splits()})
         keys = ops.transpose12(x)
         if speaker_embed_btc is not None:
             keys = keys + F.softsign(self.speaker_fc2(speaker_embed_btc))
@@ -121,10 +125,20 @@ class AttentionLayer(nn.Module):
 
     def forward(self, query, encoder_out, mask=None, last_attended=None):
         """Reference signature: query (B,Td,C); encoder_out = (keys (B,E,Ts) pre-transposed, values (B,Ts,E))."""
-        if last_attended is not None:
-            raise NotImplementedError("the attention window (last_attended) is applied by the incremental step kernel "
-                                      "(incremental.py); the batch forward has no windowed mode")
         keys, values = encoder_out
+        if last_attended is not None:
+            # reference deepvoice3.py:150-156: scores outside [last_attended - window_backward, last_attended +
+            # window_ahead) are set to -inf.  The window is the same for every query row, so it folds into the key mask.
+            Ts = keys.size(-1)
+            s = torch.arange(Ts, device=keys.device)
+            backward, ahead = last_attended - self.window_backward, last_attended + self.window_ahead
+            win = torch.zeros(Ts, dtype=torch.bool, device=keys.device)
+            if backward > 0:
+                win |= s < backward
+            if ahead < Ts:
+                win |= s >= ahead
+            win = win[None, :].expand(keys.size(0), Ts)
+            mask = win if mask is None else (mask.bool() | win)
         x, probs = self.forward_bct(ops.transpose12(query), keys, ops.transpose12(values), mask)
         return ops.transpose12(x), probs
 

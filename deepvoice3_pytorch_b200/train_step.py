@@ -225,7 +225,8 @@ def gradient_buckets(model, arena):
     """Bucket plan of the overlapped gradient exchange.  The backward pass finishes the post-net first, then the
     decoder, then the encoder from its last layer to its first (the encoder holds ~60 % of the parameters), so:
       "postnet"     everything under model.postnet        -- final when d(loss)/d(postnet input) exists
-      "encoder_hi"  encoder.convolutions[split:]          -- final when the gradient entering layer `split` exists
+      "encoder_hi" / "encoder_mid"  encoder.convolutions[hi:] / [mid:hi]  -- final when the gradient entering layer
+                    hi / mid exists
       "rest"        all other slices (decoder, first encoder layers, embeddings): reduced after backward()
     -> ({tag: (lo, hi)}, [rest ranges])."""
     tagged = {}
@@ -233,11 +234,13 @@ def gradient_buckets(model, arena):
     if post:
         tagged["postnet"] = post
     enc = getattr(getattr(model, "seq2seq", None), "encoder", None)
-    if enc is not None and hasattr(enc, "grad_bucket_split") and hasattr(enc, "convolutions"):
-        ps = [p for m in list(enc.convolutions)[enc.grad_bucket_split():] for p in m.parameters()]
-        r = arena.range_of(ps)
-        if r:
-            tagged["encoder_hi"] = r
+    if enc is not None and hasattr(enc, "grad_bucket_splits") and hasattr(enc, "convolutions"):
+        layers = list(enc.convolutions)
+        splits = sorted(enc.grad_bucket_splits(), key=lambda ti: ti[1])
+        for (tag, lo_i), hi_i in zip(splits, [i for _, i in splits[1:]] + [len(layers)]):
+            r = arena.range_of([p for m in layers[lo_i:hi_i] for p in m.parameters()])
+            if r:
+                tagged[tag] = r
     cuts = sorted(tagged.values())
     rest, pos = [], 0
     for lo, hi in cuts:

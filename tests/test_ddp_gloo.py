@@ -111,9 +111,10 @@ def test_gradient_bucket_plan_covers_the_arena():
         assert hi - lo == sum((p.numel() + 3) // 4 * 4 for p in model.postnet.parameters())
         if "encoder_hi" in tagged:
             enc = model.seq2seq.encoder
-            first = list(enc.convolutions)[enc.grad_bucket_split()]
-            p0 = next(first.parameters())
-            assert p0.data_ptr() == arena.flat[tagged["encoder_hi"][0]:].data_ptr()
+            assert "encoder_mid" in tagged and tagged["encoder_mid"][1] == tagged["encoder_hi"][0]
+            for tag, idx in enc.grad_bucket_splits():
+                p0 = next(list(enc.convolutions)[idx].parameters())
+                assert p0.data_ptr() == arena.flat[tagged[tag][0]:].data_ptr()
 
 
 def _bucket_worker(rank, world, port, ret):

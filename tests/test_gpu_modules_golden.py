@@ -109,3 +109,21 @@ def test_sinusoidal_encoding_per_utterance_rates():
     mod = mod.cuda()
     out = mod(torch.from_numpy(case["in"]["x"]).cuda(), torch.from_numpy(case["meta"]["w"]).cuda())
     close(out, case["out"]["0"], rtol=1e-5, atol=2e-6)
+
+
+def test_attention_window_last_attended():
+    """reference deepvoice3.py:150-156: with last_attended = n only keys in [n - window_backward, n + window_ahead) get
+    probability mass, in the batch forward too; result equals the oracle's masked softmax."""
+    from deepvoice3_pytorch_b200.deepvoice3 import AttentionLayer
+    case = BLOCKS["attn1"]
+    mod = AttentionLayer(48, 32, dropout=0.0, key_projection=False, value_projection=False, window_ahead=3,
+                         window_backward=1)
+    mod.load_state_dict(G.tensors(case["sd"]))
+    mod = mod.cuda().eval()
+    ins = G.tensors(case["in"], "cuda")
+    with torch.no_grad():
+        _, probs = mod(ins["query"], (ins["keys"], ins["values"]), mask=None, last_attended=5)
+        _, full = mod(ins["query"], (ins["keys"], ins["values"]), mask=None)
+    assert float(probs[:, :, :4].abs().max()) == 0.0 and float(probs[:, :, 8:].abs().max()) == 0.0
+    want = full[:, :, 4:8] / full[:, :, 4:8].sum(-1, keepdim=True)
+    close(probs[:, :, 4:8], want, rtol=1e-4, atol=1e-6)
