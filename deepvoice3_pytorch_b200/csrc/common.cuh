@@ -87,18 +87,14 @@ __device__ __forceinline__ float drop_scale(const DropCfg& d, uint32_t idx) {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ---- 16-bit operand planes of the tensor-core path -----------------------------------------------------------
-// Every fp32 operand x travels as two fp16 planes: hi = rn16(x), lo = rn16((x - hi) * 2^11).  The products
+// Every fp32 operand x travels as two 16-bit planes: hi = rn16(x), lo = rn16((x - hi) * 2^11).  The products
 // hi*hi (main accumulator) and hi*lo + lo*hi (cross accumulator, carrying the 2^11) are summed as
-// main + cross * 2^-11 by the epilogue: 11 + 11 significant bits per operand, products exact to ~2^-22 -- fp32-class
-// results from three fp16 MMA passes.  The 2^11 keeps lo out of the fp16 subnormals.
-//   forward operands (activations O(1), normalised weights) are stored as they are, clamped to the fp16 range;
-//   GRADIENT operands (magnitudes 1e-9 .. 1e-2) are stored multiplied by GRAD_SCALE = 2^10 and the GEMM epilogues
-//   that consume them multiply their result by 2^-10 (powers of two: exact).  Representable: |g| < 64 (saturates
-//   beyond), full 22-bit precision down to |g| ~ 6e-8, >= 11 bits down to ~1e-11 (the scaled lo plane keeps
-//   resolving below the fp16 subnormal threshold of hi).  tcgen05 kind::f16 cannot mix fp16 with bf16 operands, so
-//   everything is fp16; FMT_BF16 (8 + 8 bits, fp32 exponent range) remains for the in-kernel splits of tc_attn.cu.
+// main + cross * 2^-11 by the epilogue.  Two formats:
+//   FMT_F16   forward operands (activations O(1), normalised weights): fp16 hi carries 11 significant bits, the scaled
+//             fp16 lo another 11 -> 22-bit operands, products exact to ~2^-23: fp32-class results.  Values are clamped
+//             to the fp16 range (+-65504); the scale keeps lo out of the fp16 subnormals.
+//   FMT_BF16  gradients (magnitudes down to 1e-10: need the fp32 exponent range): 8 + 8 bits, products to ~2^-17.
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
-constexpr float GRAD_SCALE = 1024.f, GRAD_INV = 1.f / 1024.f;
 enum { FMT_BF16 = 2, FMT_F16 = 16 };
 template <int FMT>
 __device__ __forceinline__ void split_pair(float v, uint16_t& hi, uint16_t& lo) {

@@ -43,7 +43,8 @@ constexpr int EPI_STAGING = 2 * EPI_BUF;
 enum { TC_GATED = 0, TC_CONV = 1 };
 enum { POST_NONE = 0, POST_GLU = 1, POST_HIGHWAY = 2, POST_RELU = 3, POST_IDENT = 4 };
 
-struct TcMaps { CUtensorMap a[2]; CUtensorMap b[2]; CUtensorMap st[2]; };   // st: planes written by the epilogue (hi, lo)
+struct TcMaps { CUtensorMap a[2]; CUtensorMap b[2]; CUtensorMap st[4]; };   // st: planes written by the epilogue
+                                                                            // (hi, lo) [+ (hi, lo) of the bf16 copy]
 
 struct TcParams {
     int T, B;
@@ -60,7 +61,7 @@ struct TcParams {
     float* out; const float* e1; const float* e2; float alpha; int addmode, relu;
     float p_drop; const unsigned long long* seed_ptr; uint32_t salt;
     // forward fusion: planes of (output * next dropout mask) for the consumer conv, [2][B][T][np_pitch]
-    __nv_bfloat16* np; int np_pitch; long long np_plane;
+    __nv_bfloat16* np; int np_pitch; long long np_plane; int np_wg;    // np_wg: also emit the bf16 pair (maps.st[2..3])
     float np_p; const unsigned long long* np_seed; uint32_t np_salt;
     // backward fusion: producer backward applied to the data gradient this launch computes
     int post_kind, post_residual, post_pitch;
@@ -71,8 +72,8 @@ struct TcParams {
     // running sum; over the n_mma events of one output that is a systematic shrink of ~gcoef * n_mma (measured,
     // tools/precision_presets.py).  The epilogue multiplies the main accumulator by gmain = 1 + gcoef * n_mma (the
     // cross-term accumulator is 2^-8 smaller: its loss is below fp32 resolution).
-    float gmain;               // multiplies the main accumulator: (1 + gcoef * n_mma) [* GRAD_INV in a data gradient]
-    float gcross;              // multiplies the cross accumulator: LO_INV [* GRAD_INV]
+    float gmain;
+    uint32_t idesc_fmt;        // a_format / b_format bits of the instruction descriptor (fp16 forward, bf16 gradients)
 };
 
 template <int BK> struct SwizzleOf;
@@ -102,13 +103,13 @@ struct TcCfg {
 };
 
 // main + cross accumulator -> registers, summed in fp32 (round-to-nearest)
-// main * gmain + cross * gcross (TcParams): truncation compensation, the 2^-11 of the lo planes, the 2^-10 of gradients
-__device__ __forceinline__ void tmem_ld_add(uint32_t taddr, int cross_off, float* v, float gmain, float gcross) {
+// gmain = 1 + (expected relative truncation loss of the main accumulator), see TcParams::gmain
+__device__ __forceinline__ void tmem_ld_add(uint32_t taddr, int cross_off, float* v, float gmain) {
     float c[32];
     tmem_ld_32x32(taddr, v);
     tmem_ld_32x32(taddr + cross_off, c);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaf(c[i], gcross, v[i] * gmain);
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(c[i], LO_INV, v[i] * gmain);       // lo planes carry a 2^11 scale
 }
 
 // ---- operand planes written by the epilogues: registers -> shared-memory staging -> TMA tensor store ---------------
@@ -137,7 +138,7 @@ struct EpiStage {
 
 // One use = one [128 rows][32 channels] tile of one output tensor: FMT_F16 (forward operand) or FMT_BF16 (gradient).
 template <int FMT>
-__device__ __forceinline__ void epi_emit(EpiStage& es, int row, const float* v, int c0, int t0, int b) {
+__device__ __forceinline__ void epi_emit(EpiStage& es, int row, const float* v, int c0, int t0, int b, int map0 = 0) {
     uint8_t* buf = es.base + (es.uses & 1) * EPI_BUF;
     __syncwarp();                                        // bar.sync needs converged warps
     if (es.issuer) bulk_wait_read<1>();                  // the group that last read this buffer has drained
@@ -162,8 +163,8 @@ __device__ __forceinline__ void epi_emit(EpiStage& es, int row, const float* v, 
     __syncwarp();
     epi_bar();
     if (es.issuer) {
-        tma_store_3d(&es.map[0], buf, c0, t0, b);
-        tma_store_3d(&es.map[1], buf + 8192, c0, t0, b);
+        tma_store_3d(&es.map[map0], buf, c0, t0, b);
+        tma_store_3d(&es.map[map0 + 1], buf + 8192, c0, t0, b);
         bulk_commit();
     }
     ++es.uses;
@@ -207,8 +208,8 @@ __device__ __forceinline__ void epilogue_gated(const TcParams& p, uint32_t taddr
     const DropCfg nd = make_drop(p.np ? p.np_p : 0.f, p.np_seed, p.np_salt);
     for (int c32 = 0; c32 < BR; c32 += 32) {
         float va[32], vb[32], rr[32];
-        tmem_ld_add(taddr + c32, NCOLS, va, p.gmain, p.gcross);
-        tmem_ld_add(taddr + BR + c32, NCOLS, vb, p.gmain, p.gcross);
+        tmem_ld_add(taddr + c32, NCOLS, va, p.gmain);
+        tmem_ld_add(taddr + BR + c32, NCOLS, vb, p.gmain);
         if (tv) {
             const size_t cb = base + (size_t)c32 * p.T;
 #pragma unroll
@@ -237,7 +238,10 @@ __device__ __forceinline__ void epilogue_gated(const TcParams& p, uint32_t taddr
             }
         }
         // all 128 epilogue threads reach the emission together (named barriers inside); rows >= T are clipped by TMA
-        if (p.np) epi_emit<FMT_F16>(es, row, va, b_row0 + c32, a_row0, b);
+        if (p.np) {
+            epi_emit<FMT_F16>(es, row, va, b_row0 + c32, a_row0, b);
+            if (p.np_wg) epi_emit<FMT_BF16>(es, row, va, b_row0 + c32, a_row0, b, 2);
+        }
     }
 }
 
@@ -259,7 +263,7 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t taddr,
     const float gs = (kind == POST_GLU && p.post_residual) ? 0.70710678118654752f : 1.f;
     for (int c32 = 0; c32 < NCOLS; c32 += 32) {
         float v[32], x1[32], x2[32];
-        tmem_ld_add(taddr + c32, NCOLS, v, p.gmain, p.gcross);
+        tmem_ld_add(taddr + c32, NCOLS, v, p.gmain);
         const int n0 = b_row0 + c32;
         const size_t cb = ((size_t)b * p.Nc + n0) * p.T + (tv ? t : 0);
         if (tv) {
@@ -293,6 +297,7 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t taddr,
 #pragma unroll
             for (int i = 0; i < 32; ++i) w[i] = v[i] * drop_scale(nd, (uint32_t)(cb + (size_t)i * p.T));
             epi_emit<FMT_F16>(es, row, w, n0, a_row0, b);
+            if (p.np_wg) epi_emit<FMT_BF16>(es, row, w, n0, a_row0, b, 2);
         }
         if (kind != POST_NONE) {                            // backward of the producer of this gradient's tensor
             // v[i] = dL/d(producer output) at (b, n0+i, t) (0 outside the tile).  Gate kinds emit [da | db] planes of
@@ -307,16 +312,16 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t taddr,
                         av = __ldg(&pa[idx]); sv = __ldg(&ps[idx]);
                         if (kind == POST_HIGHWAY) xv = __ldg(&px[idx]);
                     }
-                    const float g = v[i] * gs * GRAD_SCALE;            // gradient planes carry GRAD_SCALE
+                    const float g = v[i] * gs;
                     da[i] = g * sv;
                     db[i] = g * (kind == POST_GLU ? av : (av - xv)) * sv * (1.f - sv);
                 }
-                epi_emit<FMT_F16>(es, row, da, n0, a_row0, b);
-                epi_emit<FMT_F16>(es, row, db, p.Nc + n0, a_row0, b);
+                epi_emit<FMT_BF16>(es, row, da, n0, a_row0, b);
+                epi_emit<FMT_BF16>(es, row, db, p.Nc + n0, a_row0, b);
                 const float sa = warp_colsum32(da, lane), sb = warp_colsum32(db, lane);
                 if (p.post_dbias && n0 + lane < p.Nc) {
-                    atomicAdd(&p.post_dbias[n0 + lane], sa * GRAD_INV);
-                    atomicAdd(&p.post_dbias[p.Nc + n0 + lane], sb * GRAD_INV);
+                    atomicAdd(&p.post_dbias[n0 + lane], sa);
+                    atomicAdd(&p.post_dbias[p.Nc + n0 + lane], sb);
                 }
             } else {
 #pragma unroll
@@ -326,11 +331,11 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t taddr,
                         const bool on = tv && n0 + i < p.Nc && __ldg(&pa[cb + (size_t)i * p.T]) > 0.f;
                         g = on ? g : 0.f;
                     }
-                    da[i] = g * GRAD_SCALE;
+                    da[i] = g;
                 }
-                epi_emit<FMT_F16>(es, row, da, n0, a_row0, b);
+                epi_emit<FMT_BF16>(es, row, da, n0, a_row0, b);
                 const float sa = warp_colsum32(da, lane);
-                if (p.post_dbias && n0 + lane < p.Nc) atomicAdd(&p.post_dbias[n0 + lane], sa * GRAD_INV);
+                if (p.post_dbias && n0 + lane < p.Nc) atomicAdd(&p.post_dbias[n0 + lane], sa);
             }
         }
     }
@@ -363,6 +368,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     if (threadIdx.x == 0) {
         prefetch_tmap(&maps.a[0]); prefetch_tmap(&maps.a[1]); prefetch_tmap(&maps.b[0]); prefetch_tmap(&maps.b[1]);
         if (p.np || p.post_kind) { prefetch_tmap(&maps.st[0]); prefetch_tmap(&maps.st[1]); }
+        if (p.np_wg) { prefetch_tmap(&maps.st[2]); prefetch_tmap(&maps.st[3]); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
         fence_barrier_init();
@@ -408,8 +414,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             }
         }
     } else if (warp == 1 && lane == 0) {
-        constexpr uint32_t FMT = IDESC_A_F16 | IDESC_B_F16;
-        constexpr uint32_t idesc = make_idesc_mn(128, NCOLS) | FMT, idesc2 = make_idesc_mn(128, 2 * NCOLS) | FMT;
+        const uint32_t idesc = make_idesc_mn(128, NCOLS) | p.idesc_fmt, idesc2 = make_idesc_mn(128, 2 * NCOLS) | p.idesc_fmt;
         int it = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const int a = tcount & 1, aph = (tcount >> 1) & 1;
@@ -542,8 +547,8 @@ tc_wgrad_mn_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ 
             }
         }
     } else if (warp == 1 && lane == 0) {
-        // A = gradient planes (x GRAD_SCALE), B = forward operand planes, all fp16; both MN-major
-        constexpr uint32_t idesc = make_idesc_mn(128, NCOLS) | IDESC_A_F16 | IDESC_B_F16 | (1u << 15) | (1u << 16);
+        // A = gradient planes, B = the bf16 copy of the forward operand planes; both MN-major
+        constexpr uint32_t idesc = make_idesc_bf16(128, NCOLS) | (1u << 15) | (1u << 16);
         for (int it = 0; it < n_iters; ++it) {
             const int s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(&full[s], ph);
@@ -576,7 +581,7 @@ tc_wgrad_mn_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ 
                          (((ma + (size_t)wg_j * p.s_j + (size_t)wg_split * p.split_stride) & 3) == 0);
         for (int c32 = 0; c32 < NCOLS; c32 += 32) {
             float v[32];
-            tmem_ld_add(taddr + c32, NCOLS, v, (1.f + p.gcoef * (float)(2 * n_iters)) * GRAD_INV, LO_INV * GRAD_INV);
+            tmem_ld_add(taddr + c32, NCOLS, v, 1.f + p.gcoef * (float)(2 * n_iters));
             if (m >= p.Mw) continue;
             const int nn = n0 + c32;
             if (n_iters == 0) {
@@ -690,9 +695,9 @@ int dv3_tc_conv_supported(int B, int Cin, int Cout, int T, int k) {
 }
 
 // planes written by the epilogue: [2][B][T][pitch], stored as [128 rows][32 channels] boxes (SWIZZLE_64B staging)
-static int encode_store_maps(TcMaps& maps, void* planes, int pitch, int B, int T) {
+static int encode_store_maps(TcMaps& maps, int first, void* planes, int pitch, int B, int T) {
     for (int pl = 0; pl < 2; ++pl)
-        if (encode_tmap_bf16_3d(&maps.st[pl], plane(planes, pl, (long long)B * T * pitch), pitch, T, B,
+        if (encode_tmap_bf16_3d(&maps.st[first + pl], plane(planes, pl, (long long)B * T * pitch), pitch, T, B,
                                 (uint64_t)pitch * 2, (uint64_t)T * pitch * 2, 32, 128)) return 1;
     return 0;
 }
@@ -705,7 +710,11 @@ static int apply_fuse(TcParams& p, TcMaps& maps, const Dv3TcFuse* f, int B, int 
                     what, f->np_pitch, out_channels);
         p.np = (__nv_bfloat16*)f->np; p.np_pitch = f->np_pitch; p.np_plane = (long long)B * T * f->np_pitch;
         p.np_p = f->np_p; p.np_seed = f->np_seed; p.np_salt = f->np_salt;
-        if (encode_store_maps(maps, f->np, f->np_pitch, B, T)) return 1;
+        if (encode_store_maps(maps, 0, f->np, f->np_pitch, B, T)) return 1;
+        if (f->np_wg) {
+            p.np_wg = 1;
+            if (encode_store_maps(maps, 2, f->np_wg, f->np_pitch, B, T)) return 1;
+        }
     }
     if (f->post_kind != POST_NONE) {
         DV3_REQUIRE(f->post_kind >= POST_GLU && f->post_kind <= POST_IDENT && f->post_planes, "%s: bad post_kind %d",
@@ -720,7 +729,7 @@ static int apply_fuse(TcParams& p, TcMaps& maps, const Dv3TcFuse* f, int B, int 
         p.post_pitch = gate ? 2 * out_channels : (out_channels + 7) / 8 * 8;
         p.post_plane = (long long)B * T * p.post_pitch;
         p.post_dbias = f->post_dbias;
-        if (encode_store_maps(maps, f->post_planes, p.post_pitch, B, T)) return 1;
+        if (encode_store_maps(maps, 0, f->post_planes, p.post_pitch, B, T)) return 1;
     }
     return 0;
 }
@@ -746,7 +755,7 @@ int dv3_tc_convblock_fwd(const void* xd, const void* w, int npl, const float* bi
     p.bias = bias; p.spk = spk; p.res = res; p.y = y; p.save_a = save_a; p.save_s = save_s;
     p.gate_mode = mode; p.residual = residual;
     p.gmain = 1.f + config().tc_gamma * (float)(p.k * p.kb_n * 4);
-    p.gcross = LO_INV;
+    p.idesc_fmt = IDESC_A_F16 | IDESC_B_F16;                     // forward operands: fp16 hi/lo planes
     if (apply_fuse(p, maps, fuse, B, T, C, "tc_convblock_fwd")) return 1;
     DV3_REQUIRE(p.post_kind == POST_NONE, "tc_convblock_fwd: post_kind is a data-gradient option");
     return launch_conv<TC_GATED, 2, 64, 64>(maps, p, t_tiles, C / 64, B, (cudaStream_t)stream, "tc_convblock_fwd");
@@ -783,10 +792,9 @@ int dv3_tc_conv(const void* a, const void* w, int npl, float* out, int B, int Kc
     fill_taps_tc(p.tap_off, k, dilation, causal, transpose_taps != 0);
     p.out = out; p.bias = bias; p.relu = relu; p.e1 = e1; p.e2 = e2; p.alpha = alpha; p.addmode = addmode;
     p.p_drop = p_drop; p.seed_ptr = seed_ptr; p.salt = salt;
-    // a data gradient reads gradient planes that carry GRAD_SCALE: undo it here (power of two: exact)
-    const float os = transpose_taps ? GRAD_INV : 1.f;
-    p.gmain = (1.f + config().tc_gamma * (float)(p.k * p.kb_n * (bk / 16))) * os;
-    p.gcross = LO_INV * os;
+    p.gmain = 1.f + config().tc_gamma * (float)(p.k * p.kb_n * (bk / 16));
+    // forward conv: fp16 activation x fp16 weight planes; data gradient: bf16 gradient x bf16 weight planes
+    p.idesc_fmt = transpose_taps ? (IDESC_A_BF16 | IDESC_B_BF16) : (IDESC_A_F16 | IDESC_B_F16);
     if (apply_fuse(p, maps, fuse, B, T, Nc, "tc_conv")) return 1;
     const int tiles_y = (Nc + br - 1) / br;
     if (narrow) {

@@ -1,6 +1,7 @@
-// Operand preparation for the tensor-core path (tc_gemm.cu): every fp32 operand x becomes bf16 planes
-// p0 = bf16(x), p1 = bf16(x - p0) [, p2 = bf16(x - p0 - p1)], written in the K-major layout each implicit GEMM
-// consumes.  These passes are pure HBM streaming (read 4 B, write 4-12 B per element) and absorb work the fp32 path
+// Operand preparation for the tensor-core path (tc_gemm.cu): every fp32 operand x becomes a 16-bit (hi, lo * 2^11) pair
+// (common.cuh: fp16 pairs for forward operands, bf16 pairs for gradients), written in the (B,T,C) layout each implicit
+// GEMM consumes (K-major for the forward / data gradient, MN-major for the weight gradient).  These passes are pure HBM
+// streaming and absorb work the fp32 path
 // does inside its loaders: the conv-input dropout mask, the ReLU mask of the incoming gradient, the bias-gradient
 // reduction and the (B,C,T) <-> (B,T,C) layout change.  Channel pitches are padded to a multiple of 8 (16 bytes,
 // the TMA stride granularity); pad columns are never read (the tensor maps carry the true extent).
@@ -10,100 +11,135 @@
 
 namespace dv3 {
 
-// x (B,C,T) fp32 -> conv-input dropout -> (hi, lo) fp16 planes in (B,T,Cp): the forward GEMM's K-major operand and
-// the weight gradient's MN-major operand.  32(c) x 32(t) tile per CTA, block (32, 8).
-__global__ void split_input_kernel(const float* __restrict__ x, bf16* __restrict__ btc, int Bn, int C, int Cp, int T,
-                                   float p, const unsigned long long* __restrict__ seed_ptr, unsigned salt) {
-    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
-    __shared__ float tile[32][33];
-    const DropCfg drop = make_drop(p, seed_ptr, salt);
-    const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = c0 + threadIdx.y + 8 * i, t = t0 + threadIdx.x;
-        float v = 0.f;
-        if (c < C && t < T) {
-            const size_t row = ((size_t)b * C + c) * T;
-            v = x[row + t] * drop_scale(drop, (uint32_t)(row + t));
-        }
-        tile[threadIdx.y + 8 * i][threadIdx.x] = v;
-    }
-    __syncthreads();
-    const size_t btc_plane = (size_t)Bn * T * Cp;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
-        if (c < C && t < T)
-            split_store<FMT_F16>(tile[threadIdx.x][threadIdx.y + 8 * i], btc, ((size_t)b * T + t) * Cp + c, btc_plane);
-    }
-}
+// ---- activation-side operand preparation: ONE kernel template, three uses ------------------------------------
+//   SPLIT_INPUT  x (B,C,T) -> conv-input dropout -> fp16 planes (B,T,Cp) [forward operand] and, when wg != NULL, the same
+//                values as a bf16 pair [operand of the weight gradient, which multiplies them with bf16 gradient
+//                planes: tcgen05 kind::f16 cannot mix fp16 and bf16 operands in one MMA]
+//   SPLIT_GATE   gate backward (conv.cu gate_bwd_kernel) of dy with the saved a, s (, x) -> dAB = [da | db] as bf16
+//                planes (B,T,2C); dbias[2C] += sums over (b,t)                           [data-/weight-gradient operand]
+//   SPLIT_GRAD   g = dy * (relu ? y > 0 : 1) -> bf16 planes (B,T,Cp); dbias[C] += sums
+// A CTA (256 threads) owns 64 channels x 64 time steps of one utterance: float4 loads along T (16 threads per channel
+// row, 3-4 tensors in flight per thread), bias-gradient sums reduced across those 16 lanes (one atomic per row and
+// tile), transpose through shared memory, and 16-byte stores of 8 channels per thread -- 8 threads cover the 128
+// contiguous bytes of one (b,t) row of a plane.  (The round-1 kernels used 32x32 tiles with 2-byte stores, 64 B per
+// warp-store row: 25 % of the HBM roof over a training step.)
+enum { SPLIT_INPUT = 0, SPLIT_GATE = 1, SPLIT_GRAD = 2 };
 
-// gate backward (see conv.cu gate_bwd_kernel) producing dAB = [da ; db] * GRAD_SCALE directly as 2 fp16 planes in
-// (B,T,2C) [data-gradient operand] and (B,2C,T) [weight-gradient operand]; dbias[2C] += sums over (b,t).
-__global__ void gate_bwd_split_kernel(const float* __restrict__ dy, const float* __restrict__ a,
-                                      const float* __restrict__ s, const float* __restrict__ x,
-                                      bf16* __restrict__ btc, float* __restrict__ dbias, int Bn, int C, int T, int mode,
-                                      int residual) {
-    pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
-    __shared__ float ta[32][33], tb[32][33];
-    const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
-    const float gs = (mode == 0 && residual) ? 0.70710678118654752f : 1.f;
-    const size_t plane = (size_t)Bn * 2 * C * T;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = c0 + threadIdx.y + 8 * i, t = t0 + threadIdx.x;
-        float da = 0.f, db = 0.f;
-        if (c < C && t < T) {
-            const size_t in = ((size_t)b * C + c) * T + t;
-            const float g = dy[in] * gs, av = a[in], sv = s[in];
-            da = g * sv;
-            db = g * ((mode == 0) ? av : (av - x[in])) * sv * (1.f - sv);
-        }
-        ta[threadIdx.y + 8 * i][threadIdx.x] = da;
-        tb[threadIdx.y + 8 * i][threadIdx.x] = db;
-        // bias gradient: reduce this row's 32 time steps across the warp (threadIdx.x = lane)
-        const float sa = warp_sum(da), sb = warp_sum(db);
-        if (threadIdx.x == 0 && c < C && dbias) { atomicAdd(&dbias[c], sa); atomicAdd(&dbias[C + c], sb); }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
-        if (c < C && t < T) {
-            const size_t o = ((size_t)b * T + t) * 2 * C + c;
-            split_store<FMT_F16>(ta[threadIdx.x][threadIdx.y + 8 * i] * GRAD_SCALE, btc, o, plane);
-            split_store<FMT_F16>(tb[threadIdx.x][threadIdx.y + 8 * i] * GRAD_SCALE, btc, o + C, plane);
-        }
-    }
-}
+struct SplitParams {
+    const float* in0;          // x | dy | dy
+    const float* in1;          // - | a  | y (relu) or null
+    const float* in2;          // - | s  | -
+    const float* in3;          // - | x (highway) | -
+    bf16* planes;              // [2][B][T][pitch]
+    bf16* wg;                  // SPLIT_INPUT: bf16 copy [2][B][T][pitch] or null
+    float* dbias;              // null | [2C] | [C]
+    int B, C, T, pitch;
+    int mode, residual, relu;  // gate mode (0 GLU, 1 highway), GLU residual flag; ReLU flag
+    float p; const unsigned long long* seed_ptr; unsigned salt;     // SPLIT_INPUT dropout
+};
 
-// plain conv backward prologue: g = dy * (relu ? y > 0 : 1) -> 2 planes in (B,T,Cp) and (B,C,T); dbias[C] += sums.
-__global__ void grad_split_kernel(const float* __restrict__ dy, const float* __restrict__ y, bf16* __restrict__ btc,
-                                  float* __restrict__ dbias, int Bn, int C, int Cp, int T, int relu) {
+template <int KIND>
+__global__ void __launch_bounds__(256) plane_split_kernel(const __grid_constant__ SplitParams p) {
     pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+    __shared__ float sa[64][65];
+    __shared__ float sb[KIND == SPLIT_GATE ? 64 : 1][65];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z, c0 = blockIdx.y * 64, t0 = blockIdx.x * 64;
+    const int C = p.C, T = p.T;
+    const bool vec = (T & 3) == 0;
+    const DropCfg drop = make_drop(KIND == SPLIT_INPUT ? p.p : 0.f, p.seed_ptr, p.salt);
+    const float gs = (KIND == SPLIT_GATE && p.mode == 0 && p.residual) ? 0.70710678118654752f : 1.f;
+    const int q = tid & 15;                                  // float4 slot along T
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = c0 + threadIdx.y + 8 * i, t = t0 + threadIdx.x;
-        float g = 0.f;
+    for (int j = 0; j < 4; ++j) {
+        const int r = (tid >> 4) + 16 * j, c = c0 + r, t = t0 + 4 * q;
+        float v0[4] = {0.f, 0.f, 0.f, 0.f}, v1[4] = {0.f, 0.f, 0.f, 0.f};
         if (c < C && t < T) {
-            const size_t in = ((size_t)b * C + c) * T + t;
-            g = dy[in];
-            if (relu && !(y[in] > 0.f)) g = 0.f;
+            const size_t row = ((size_t)b * C + c) * T + t;
+            float x0[4], x1[4], x2[4], x3[4];
+            const bool full = vec && t + 3 < T;
+            auto ld = [&](const float* src, float* dst) {
+                if (full) {
+                    const float4 u = __ldg(reinterpret_cast<const float4*>(src + row));
+                    dst[0] = u.x; dst[1] = u.y; dst[2] = u.z; dst[3] = u.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dst[e] = (t + e < T) ? __ldg(src + row + e) : 0.f;
+                }
+            };
+            ld(p.in0, x0);
+            if (KIND == SPLIT_GATE) { ld(p.in1, x1); ld(p.in2, x2); if (p.mode != 0) ld(p.in3, x3); }
+            if (KIND == SPLIT_GRAD && p.relu) ld(p.in1, x1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (KIND == SPLIT_INPUT) {
+                    v0[e] = x0[e] * drop_scale(drop, (uint32_t)(row + e));
+                } else if (KIND == SPLIT_GATE) {
+                    const float g = x0[e] * gs, av = x1[e], sv = x2[e];
+                    v0[e] = g * sv;
+                    v1[e] = g * (p.mode == 0 ? av : (av - x3[e])) * sv * (1.f - sv);
+                } else {
+                    v0[e] = (p.relu && !(x1[e] > 0.f)) ? 0.f : x0[e];
+                }
+                if (t + e >= T) { v0[e] = 0.f; v1[e] = 0.f; }
+            }
         }
-        tile[threadIdx.y + 8 * i][threadIdx.x] = g;
-        const float sg = warp_sum(g);
-        if (threadIdx.x == 0 && c < C && dbias) atomicAdd(&dbias[c], sg);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            sa[r][4 * q + e] = v0[e];
+            if (KIND == SPLIT_GATE) sb[r][4 * q + e] = v1[e];
+        }
+        if (KIND != SPLIT_INPUT && p.dbias) {                // all 32 lanes take part: 16 lanes share a channel row
+            float s0 = v0[0] + v0[1] + v0[2] + v0[3], s1 = v1[0] + v1[1] + v1[2] + v1[3];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                if (KIND == SPLIT_GATE) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            }
+            if (q == 0 && c < C) {
+                atomicAdd(&p.dbias[c], s0);
+                if (KIND == SPLIT_GATE) atomicAdd(&p.dbias[C + c], s1);
+            }
+        }
     }
     __syncthreads();
-    if (btc) {
+    constexpr int FMT = KIND == SPLIT_INPUT ? FMT_F16 : FMT_BF16;
+    const size_t plane = (size_t)p.B * T * p.pitch;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int t = t0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
-            if (c < C && t < T)
-                split_store<FMT_F16>(tile[threadIdx.x][threadIdx.y + 8 * i] * GRAD_SCALE, btc,
-                                     ((size_t)b * T + t) * Cp + c, (size_t)Bn * T * Cp);
+    for (int j = 0; j < 2; ++j) {
+        const int slot = tid + 256 * j, tt = slot >> 3, cg = slot & 7, t = t0 + tt, c = c0 + cg * 8;
+        if (t >= T || c >= (KIND == SPLIT_GATE ? C : p.pitch)) continue;
+        const size_t off = ((size_t)b * T + t) * p.pitch + c;
+#pragma unroll
+        for (int half = 0; half < (KIND == SPLIT_GATE ? 2 : 1); ++half) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = half ? sb[(cg * 8 + i) % 64][tt] : sa[cg * 8 + i][tt];
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint16_t h0, l0, h1, l1;
+                split_pair<FMT>(e[2 * i], h0, l0);
+                split_pair<FMT>(e[2 * i + 1], h1, l1);
+                h[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                l[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+            uint16_t* d = reinterpret_cast<uint16_t*>(p.planes) + off + (half ? C : 0);
+            *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(d + plane) = make_uint4(l[0], l[1], l[2], l[3]);
+            if (KIND == SPLIT_INPUT && p.wg) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint16_t h0, l0, h1, l1;
+                    split_pair<FMT_BF16>(e[2 * i], h0, l0);
+                    split_pair<FMT_BF16>(e[2 * i + 1], h1, l1);
+                    h[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                    l[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                }
+                uint16_t* w = reinterpret_cast<uint16_t*>(p.wg) + off;
+                *reinterpret_cast<uint4*>(w) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(w + plane) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
         }
     }
 }
@@ -134,39 +170,45 @@ using namespace dv3;
 
 extern "C" {
 
+static dim3 split_grid(int B, int C, int T) { return dim3((T + 63) / 64, (C + 63) / 64, B); }
+
 int dv3_tc_split_input(const float* x, void* btc, int npl, void* bct, int B, int C, int T, int k, int dilation,
                        int causal, float p_drop, const unsigned long long* seed_ptr, unsigned salt, void* stream) {
-    DV3_REQUIRE(B <= 65535 && (C + 31) / 32 <= 65535, "tc_split_input: grid too large");
-    DV3_REQUIRE(npl == 2 && bct == nullptr, "tc_split_input: npl must be 2 and bct NULL (the weight gradient reads btc)");
+    DV3_REQUIRE(B <= 65535 && (C + 63) / 64 <= 65535, "tc_split_input: grid too large");
+    DV3_REQUIRE(npl == 2, "tc_split_input: npl must be 2");
     (void)k; (void)dilation; (void)causal;
-    const int Cp = (C + 7) / 8 * 8;
-    dim3 grid((T + 31) / 32, (C + 31) / 32, B);
-    launch_k(split_input_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, x, (bf16*)btc, B, C, Cp, T, p_drop, seed_ptr,
-             salt);
+    SplitParams p = {};
+    p.in0 = x; p.planes = (bf16*)btc; p.wg = (bf16*)bct; p.B = B; p.C = C; p.T = T; p.pitch = (C + 7) / 8 * 8;
+    p.p = p_drop; p.seed_ptr = seed_ptr; p.salt = salt;
+    launch_k(plane_split_kernel<SPLIT_INPUT>, split_grid(B, C, T), dim3(256), 0, (cudaStream_t)stream, p);
     return check_launch("tc_split_input");
 }
 
 int dv3_tc_gate_bwd_split(const float* dy, const float* a, const float* s, const float* x, void* btc, void* bct,
                           float* dbias, int B, int C, int T, int mode, int residual, void* stream) {
     DV3_REQUIRE(bct == nullptr, "tc_gate_bwd_split: bct must be NULL");
-    dim3 grid((T + 31) / 32, (C + 31) / 32, B);
-    launch_k(gate_bwd_split_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, dy, a, s, x, (bf16*)btc, dbias, B, C, T,
-             mode, residual);
+    DV3_REQUIRE(C % 8 == 0 && (mode == 0 || x != nullptr), "tc_gate_bwd_split: C %% 8 != 0 or highway without x");
+    SplitParams p = {};
+    p.in0 = dy; p.in1 = a; p.in2 = s; p.in3 = x; p.planes = (bf16*)btc; p.dbias = dbias;
+    p.B = B; p.C = C; p.T = T; p.pitch = 2 * C; p.mode = mode; p.residual = residual;
+    launch_k(plane_split_kernel<SPLIT_GATE>, split_grid(B, C, T), dim3(256), 0, (cudaStream_t)stream, p);
     return check_launch("tc_gate_bwd_split");
 }
 
 int dv3_tc_grad_split(const float* dy, const float* y, void* btc, void* bct, float* dbias, int B, int C, int T,
                       int relu, void* stream) {
     DV3_REQUIRE(bct == nullptr, "tc_grad_split: bct must be NULL");
-    const int Cp = (C + 7) / 8 * 8;
-    dim3 grid((T + 31) / 32, (C + 31) / 32, B);
-    launch_k(grad_split_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, dy, y, (bf16*)btc, dbias, B, C, Cp, T, relu);
+    DV3_REQUIRE(!relu || y != nullptr, "tc_grad_split: ReLU backward needs the forward output");
+    SplitParams p = {};
+    p.in0 = dy; p.in1 = y; p.planes = (bf16*)btc; p.dbias = dbias;
+    p.B = B; p.C = C; p.T = T; p.pitch = (C + 7) / 8 * 8; p.relu = relu;
+    launch_k(plane_split_kernel<SPLIT_GRAD>, split_grid(B, C, T), dim3(256), 0, (cudaStream_t)stream, p);
     return check_launch("tc_grad_split");
 }
 
 // Weight norm + split for a conv weight v (Cout, Cin, k), g [Cout]:
 //   wfwd: [2][k][Cout][Cinp] fp16 planes (forward operand: rows co, K = ci)
-//   wbwd: [2][k][Cin][Coutp] fp16 planes (data-gradient operand)
+//   wbwd: [2][k][Cin][Coutp] bf16 planes (data-gradient operand, multiplied with bf16 gradient planes)
 int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wfwd, int npl,
                           void* wbwd, int Cout, int Cin, int k, void* stream) {
     DV3_REQUIRE(npl == 2, "tc_weightnorm_fwd: npl must be 2");
@@ -176,7 +218,7 @@ int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float
     launch_k(wn_norm_kernel2, (Cout * 32 + 255) / 256, 256, 0, st, v, g, inv_norm, scale, Cout, L);
     if (int e = check_launch("tc_weightnorm_fwd(norm)")) return e;
     dim3 grid((L + 31) / 32, (Cout + 31) / 32);
-    launch_k(wn_pack_split_kernel<FMT_F16, FMT_F16>, grid, dim3(32, 8), 0, st, v, scale, (bf16*)wfwd, Cinp, 1,
+    launch_k(wn_pack_split_kernel<FMT_F16, FMT_BF16>, grid, dim3(32, 8), 0, st, v, scale, (bf16*)wfwd, Cinp, 1,
              (long long)Cout * Cinp, (long long)k * Cout * Cinp, (bf16*)wbwd, 1, Coutp, (long long)Cin * Coutp,
              (long long)k * Cin * Coutp, Cout, Cin, k);
     return check_launch("tc_weightnorm_fwd(pack)");
@@ -184,7 +226,7 @@ int dv3_tc_weightnorm_fwd(const float* v, const float* g, float* inv_norm, float
 
 // ConvTranspose1d(k=2,s=2) weight v (Cin, Cout, 2), g [Cin] (norm over dim 0 = Cin), run as a 1x1 conv with
 // 2*Cout output rows ordered (j, co):
-//   wfwd: [2][2*Cout][Cinp] fp16, rows (j,co), K = ci        wbwd: [2][Cin][K2p] fp16, rows ci, K = (j,co)
+//   wfwd: [2][2*Cout][Cinp] fp16, rows (j,co), K = ci        wbwd: [2][Cin][K2p] bf16, rows ci, K = (j,co)
 int dv3_tc_weightnorm_convt_fwd(const float* v, const float* g, float* inv_norm, float* scale, void* wfwd, int npl,
                                 void* wbwd, int Cin, int Cout, void* stream) {
     DV3_REQUIRE(npl == 2, "tc_weightnorm_convt_fwd: npl must be 2");
@@ -195,7 +237,7 @@ int dv3_tc_weightnorm_convt_fwd(const float* v, const float* g, float* inv_norm,
     if (int e = check_launch("tc_weightnorm_convt_fwd(norm)")) return e;
     dim3 grid((L + 31) / 32, (Cin + 31) / 32);
     // r = ci, x = co, j: outA (lanes along (x,j)) = wbwd [ci][j*Cout+co] ; outB (lanes along r) = wfwd [(j*Cout+co)][ci]
-    launch_k(wn_pack_split_kernel<FMT_F16, FMT_F16>, grid, dim3(32, 8), 0, st, v, scale, (bf16*)wbwd, K2p, 1,
+    launch_k(wn_pack_split_kernel<FMT_BF16, FMT_F16>, grid, dim3(32, 8), 0, st, v, scale, (bf16*)wbwd, K2p, 1,
              (long long)Cout, (long long)Cin * K2p, (bf16*)wfwd, 1, Cinp, (long long)Cout * Cinp,
              (long long)2 * Cout * Cinp, Cin, Cout, 2);
     return check_launch("tc_weightnorm_convt_fwd(pack)");

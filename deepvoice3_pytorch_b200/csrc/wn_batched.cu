@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) wn_pack_batched_kernel(const Dv3WnEntry* 
     const int lb = blockIdx.x - e.blk_pack;
     const int by = lb / e.pack_gx, bx = lb - by * e.pack_gx;
     const long long Cinp = (e.Cin + 7) / 8 * 8, Coutp = (e.Cout + 7) / 8 * 8;
-    wn_pack_split_tile<FMT_F16, FMT_F16>(e.v, e.scale, (bf16*)e.wfwd, Cinp, 1, (long long)e.Cout * Cinp,
+    wn_pack_split_tile<FMT_F16, FMT_BF16>(e.v, e.scale, (bf16*)e.wfwd, Cinp, 1, (long long)e.Cout * Cinp,
                              (long long)e.k * e.Cout * Cinp, (bf16*)e.wbwd, 1, Coutp, (long long)e.Cin * Coutp,
                              (long long)e.k * e.Cin * Coutp, e.Cout, e.Cin, e.k, bx, by, tile);
 }

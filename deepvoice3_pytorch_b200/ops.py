@@ -329,18 +329,19 @@ POST_GLU, POST_HIGHWAY, POST_RELU, POST_IDENT = 1, 2, 3, 4
 
 
 class Dv3TcFuse(ctypes.Structure):
-    _fields_ = [("np", ctypes.c_void_p), ("np_seed", ctypes.c_void_p), ("np_p", ctypes.c_float),
+    _fields_ = [("np", ctypes.c_void_p), ("np_wg", ctypes.c_void_p), ("np_seed", ctypes.c_void_p), ("np_p", ctypes.c_float),
                 ("np_salt", ctypes.c_uint), ("np_pitch", ctypes.c_int), ("post_kind", ctypes.c_int),
                 ("post_residual", ctypes.c_int), ("post_a", ctypes.c_void_p), ("post_s", ctypes.c_void_p),
                 ("post_x", ctypes.c_void_p), ("post_planes", ctypes.c_void_p), ("post_dbias", ctypes.c_void_p)]
 
 
 class Planes:
-    """Operand planes [2][B][T][pad8(C)] (fp16 pair) of (tensor * dropout mask(p, seed, salt)) written by the producer's
-    epilogue: what the consumer's forward GEMM and weight gradient read."""
+    """Operand planes of (tensor * dropout mask(p, seed, salt)) written by the producer's epilogue:
+    t = [2][B][T][pad8(C)] fp16 pair (forward GEMM operand), wg = the same values as a bf16 pair (weight-gradient
+    operand; None when the producer was told the consumer needs no backward)."""
 
-    def __init__(self, t, C, p, seed_t, salt):
-        self.t, self.C, self.p, self.seed_t, self.salt = t, C, p, seed_t, salt
+    def __init__(self, t, wg, C, p, seed_t, salt):
+        self.t, self.wg, self.C, self.p, self.seed_t, self.salt = t, wg, C, p, seed_t, salt
 
 
 class ProducerRec:
@@ -363,6 +364,7 @@ def _fuse_struct(emit=None, rec=None, dbias=None):
     if emit is not None:
         f.np, f.np_seed, f.np_p, f.np_salt = emit.t.data_ptr(), (emit.seed_t.data_ptr() if emit.seed_t is not None else None), \
             emit.p, emit.salt
+        f.np_wg = emit.wg.data_ptr() if emit.wg is not None else None
         f.np_pitch = emit.t.shape[-1]
     if rec is not None:
         f.post_kind, f.post_residual = rec.kind, int(rec.residual)
@@ -374,12 +376,15 @@ def _fuse_struct(emit=None, rec=None, dbias=None):
     return ctypes.byref(f), f
 
 
-def _new_planes(emit_p, training, B, T, C, dev):
-    """Planes buffer + dropout identity for a consumer with input dropout ``emit_p`` (None: nothing to emit)."""
+def _new_planes(emit_p, training, B, T, C, dev, need_wg):
+    """Planes buffer + dropout identity for a consumer with input dropout ``emit_p`` (None: nothing to emit).
+    need_wg: also the bf16 pair the consumer's weight gradient reads (the producer passes its own need-backward flag:
+    grad mode is off inside autograd.Function.forward, so it cannot be asked here)."""
     if emit_p is None or not fuse_fwd:
         return None
     p, seed_t, salt = _drop_args(emit_p, training, dev)
-    return Planes(torch.empty(2, B, T, _pad8(C), device=dev, dtype=torch.float16), C, p, seed_t, salt)
+    wg = torch.empty(2, B, T, _pad8(C), device=dev, dtype=torch.bfloat16) if need_wg else None
+    return Planes(torch.empty(2, B, T, _pad8(C), device=dev, dtype=torch.float16), wg, C, p, seed_t, salt)
 
 
 def _usable(xh, C, B, T, p_needed):
@@ -432,18 +437,19 @@ class _ConvBlockTCFn(torch.autograd.Function):
             inv = torch.empty(2 * C, device=dev)
             scale = torch.empty_like(inv)
             wfwd = torch.empty(2, k, 2 * C, C, device=dev, dtype=torch.float16)
-            wbwd = torch.empty(2, k, C, 2 * C, device=dev, dtype=torch.float16)
+            wbwd = torch.empty(2, k, C, 2 * C, device=dev, dtype=bf)
         p_eff = float(p_drop) if (training and p_drop > 0.0) else 0.0
         usable = _usable(xh, C, B, T, p_eff)
         if usable:                                       # the producer drew our dropout identity (salt order unchanged)
             p, seed_t, salt = xh.p, xh.seed_t, xh.salt
         else:
             p, seed_t, salt = _drop_args(p_drop, training, dev)
-        if usable:
-            x_btc = xh.t                                 # ... and already applied it to the planes it wrote
+        if usable and (xh.wg is not None or not need_bwd):
+            x_btc, x_wg = xh.t, xh.wg                    # ... and already applied it to the planes it wrote
             split = False
         else:
-            x_btc = torch.empty(2, B, T, C, device=dev, dtype=torch.float16)   # operand of the forward GEMM and of wgrad
+            x_btc = torch.empty(2, B, T, C, device=dev, dtype=torch.float16)        # forward operand (fp16 pair)
+            x_wg = torch.empty(2, B, T, C, device=dev, dtype=bf) if need_bwd else None  # weight-gradient operand
             split = True
         seed_ptr = _p(seed_t)
         y = torch.empty_like(x)
@@ -456,17 +462,17 @@ class _ConvBlockTCFn(torch.autograd.Function):
                 lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), 2, _p(wbwd), 2 * C, C,
                          k, _stream())    # the activation split below
         if split:
-            lib.call("dv3_tc_split_input", _p(x), _p(x_btc), 2, None, B, C, T, k, dilation, int(causal), p,
+            lib.call("dv3_tc_split_input", _p(x), _p(x_btc), 2, _p(x_wg), B, C, T, k, dilation, int(causal), p,
                      seed_ptr, salt, _stream())
         if side is not None:
             side.join()
-        emit = _new_planes(emit_p, training, B, T, C, dev)
+        emit = _new_planes(emit_p, training, B, T, C, dev, need_bwd)
         fptr, _keep = _fuse_struct(emit=emit)
         lib.call("dv3_tc_convblock_fwd", _p(x_btc), _p(wfwd), 2, _p(bias), _p(spk), _p(x), _p(y), _p(a), _p(s),
                  B, C, T, k, dilation, int(causal), mode, int(residual), fptr, _stream())
         rec = None
         if need_bwd:
-            ctx.save_for_backward(x, v, g, a, s, x_btc, wbwd, inv)
+            ctx.save_for_backward(x, v, g, a, s, x_wg, wbwd, inv)
             ctx.cfg = (k, dilation, causal, mode, residual, p, salt, spk is not None, dev)
             ctx.seed_t = seed_t
             ctx.bias_param = bias if bias.is_leaf else None
@@ -482,7 +488,7 @@ class _ConvBlockTCFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x, v, g, a, s, x_btc, wbwd, inv = ctx.saved_tensors
+        x, v, g, a, s, x_wg, wbwd, inv = ctx.saved_tensors
         k, dilation, causal, mode, residual, p, salt, has_spk, dev = ctx.cfg
         seed_ptr = _p(ctx.seed_t)          # the forward's own seed snapshot
         dy = _c(dy)
@@ -498,7 +504,7 @@ class _ConvBlockTCFn(torch.autograd.Function):
                 sink[2].add_(dbias)
             rec.planes = rec.a = rec.s = rec.x = None
         else:
-            d_btc = torch.empty(2, B, T, 2 * C, device=dev, dtype=torch.float16)
+            d_btc = torch.empty(2, B, T, 2 * C, device=dev, dtype=bf)
             dbias = sink[2] if sink else torch.zeros(2 * C, device=dev)
             lib.call("dv3_tc_gate_bwd_split", _p(dy), _p(a), _p(s), _p(x), _p(d_btc), None, _p(dbias), B, C, T,
                      mode, int(residual), _stream())
@@ -518,7 +524,7 @@ class _ConvBlockTCFn(torch.autograd.Function):
         if need_w:
             with side:
                 # partials [split][j][2C][C]: contiguous float4 stores from the GEMM epilogue
-                lib.call("dv3_tc_wgrad_mn", _p(d_btc), _p(x_btc), _p(partials), numel, B, 2 * C, C, T, k, dilation,
+                lib.call("dv3_tc_wgrad_mn", _p(d_btc), _p(x_wg), _p(partials), numel, B, 2 * C, C, T, k, dilation,
                          int(causal), 2 * C, C, 0, 1, 2 * C * C, _stream())
                 if not deferred:
                     _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k, out=(dv, dg), accumulate=bool(sink))
@@ -543,9 +549,8 @@ class _ConvBlockTCFn(torch.autograd.Function):
         elif dbias is None:
             dbias = torch.zeros(2 * C, device=dev)
         dspk = None
-        if has_spk and ctx.needs_input_grad[4]:     # d_a = (hi + lo * 2^-11) * 2^-10 of the (B,T,2C) planes -> (B,C,T)
-            dspk = transpose12(((d_btc[0, :, :, :C].float() + d_btc[1, :, :, :C].float() * (1.0 / 2048.0)) *
-                                (1.0 / 1024.0)).contiguous())
+        if has_spk and ctx.needs_input_grad[4]:     # d_a = hi + lo * 2^-11 of the (B,T,2C) planes, back to (B,C,T)
+            dspk = transpose12((d_btc[0, :, :, :C].float() + d_btc[1, :, :, :C].float() * (1.0 / 2048.0)).contiguous())
         return (dx, dv, dg, dbias, dspk) + (None,) * 12
 
 
@@ -567,9 +572,14 @@ class _Conv1dTCFn(torch.autograd.Function):
             inv = torch.empty(Cout, device=dev)
             scale = torch.empty_like(inv)
             wfwd = torch.empty(2, k, Cout, Cinp, device=dev, dtype=torch.float16)
-            wbwd = torch.empty(2, k, Cin, Coutp, device=dev, dtype=torch.float16)
-        split = not _usable(xh, Cin, B, T, 0.0)
-        x_btc = torch.empty(2, B, T, Cinp, device=dev, dtype=torch.float16) if split else xh.t
+            wbwd = torch.empty(2, k, Cin, Coutp, device=dev, dtype=bf)
+        need_w = need_bwd and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        split = not (_usable(xh, Cin, B, T, 0.0) and (xh.wg is not None or not need_w))
+        if split:
+            x_btc = torch.empty(2, B, T, Cinp, device=dev, dtype=torch.float16)
+            x_wg = torch.empty(2, B, T, Cinp, device=dev, dtype=bf) if need_w else None
+        else:
+            x_btc, x_wg = xh.t, xh.wg
         y = torch.empty(B, Cout, T, device=dev)
         side = None
         if bank is None:
@@ -578,17 +588,17 @@ class _Conv1dTCFn(torch.autograd.Function):
                 lib.call("dv3_tc_weightnorm_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), 2, _p(wbwd), Cout, Cin,
                          k, _stream())
         if split:
-            lib.call("dv3_tc_split_input", _p(x), _p(x_btc), 2, None, B, Cin, T, k, dilation, int(causal), 0.0,
+            lib.call("dv3_tc_split_input", _p(x), _p(x_btc), 2, _p(x_wg), B, Cin, T, k, dilation, int(causal), 0.0,
                      None, 0, _stream())
         if side is not None:
             side.join()
-        emit = _new_planes(emit_p, training, B, T, Cout, dev)
+        emit = _new_planes(emit_p, training, B, T, Cout, dev, need_bwd)
         fptr, _keep = _fuse_struct(emit=emit)
         lib.call("dv3_tc_conv", _p(x_btc), _p(wfwd), 2, _p(y), B, Cin, Cout, T, k, dilation, int(causal), 0,
                  _p(bias), int(relu), 0.0, None, 0, 0, None, None, 0.0, fptr, _stream())
         rec = None
         if need_bwd:
-            ctx.save_for_backward(v, g, x_btc, wbwd, inv, y if relu else None)
+            ctx.save_for_backward(v, g, x_wg, wbwd, inv, y if relu else None)
             ctx.cfg = (B, Cin, Cout, T, k, dilation, causal, relu)
             ctx.bias_param = bias if bias.is_leaf else None
             ctx.bank = bank
@@ -602,7 +612,7 @@ class _Conv1dTCFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        v, g, x_btc, wbwd, inv, y = ctx.saved_tensors
+        v, g, x_wg, wbwd, inv, y = ctx.saved_tensors
         B, Cin, Cout, T, k, dilation, causal, relu = ctx.cfg
         dy = _c(dy)
         dev, bf = dy.device, torch.bfloat16
@@ -618,7 +628,7 @@ class _Conv1dTCFn(torch.autograd.Function):
                 sink[2].add_(dbias)
             rec.planes = rec.a = None
         else:
-            g_btc = torch.empty(2, B, T, Coutp, device=dev, dtype=torch.float16)
+            g_btc = torch.empty(2, B, T, Coutp, device=dev, dtype=bf)
             dbias = sink[2] if sink else torch.zeros(Cout, device=dev)
             lib.call("dv3_tc_grad_split", _p(dy), _p(y), _p(g_btc), None, _p(dbias), B, Cout, T, int(relu), _stream())
         dv = dg = None
@@ -632,7 +642,7 @@ class _Conv1dTCFn(torch.autograd.Function):
                 partials = torch.empty(nsplit, numel, device=dev)
             dv, dg = (sink[0], sink[1]) if sink else (torch.empty_like(v), torch.empty_like(g))
             with side:
-                lib.call("dv3_tc_wgrad_mn", _p(g_btc), _p(x_btc), _p(partials), numel, B, Cout, Cin, T, k, dilation,
+                lib.call("dv3_tc_wgrad_mn", _p(g_btc), _p(x_wg), _p(partials), numel, B, Cout, Cin, T, k, dilation,
                          int(causal), Cout, Cin, 0, 1, Cout * Cin, _stream())
                 if not deferred:
                     _wn_bwd(partials, nsplit, v, g, inv, tap_major_k=k, out=(dv, dg), accumulate=bool(sink))
@@ -668,35 +678,36 @@ class _ConvT2TCFn(torch.autograd.Function):
         inv = torch.empty(Cin, device=dev)
         scale = torch.empty_like(inv)
         wfwd = torch.empty(2, 2 * Cout, Cinp, device=dev, dtype=torch.float16)
-        wbwd = torch.empty(2, Cin, K2p, device=dev, dtype=torch.float16)
+        wbwd = torch.empty(2, Cin, K2p, device=dev, dtype=bf)
         lib.call("dv3_tc_weightnorm_convt_fwd", _p(v), _p(g), _p(inv), _p(scale), _p(wfwd), 2, _p(wbwd), Cin, Cout,
                  _stream())
-        if _usable(xh, Cin, B, T, 0.0):
-            x_btc = xh.t
+        if _usable(xh, Cin, B, T, 0.0) and xh.wg is not None:
+            x_btc, x_wg = xh.t, xh.wg
         else:
             x_btc = torch.empty(2, B, T, Cinp, device=dev, dtype=torch.float16)
-            lib.call("dv3_tc_split_input", _p(x), _p(x_btc), 2, None, B, Cin, T, 1, 1, 0, 0.0, None, 0, _stream())
+            x_wg = torch.empty(2, B, T, Cinp, device=dev, dtype=bf)
+            lib.call("dv3_tc_split_input", _p(x), _p(x_btc), 2, _p(x_wg), B, Cin, T, 1, 1, 0, 0.0, None, 0, _stream())
         bias2 = bias.repeat(2)
         yp = torch.empty(B, 2 * Cout, T, device=dev)
         lib.call("dv3_tc_conv", _p(x_btc), _p(wfwd), 2, _p(yp), B, Cin, 2 * Cout, T, 1, 1, 0, 0, _p(bias2), 0, 0.0,
                  None, 0, 0, None, None, 0.0, None, _stream())
         y = torch.empty(B, Cout, 2 * T, device=dev)
         lib.call("dv3_interleave2", _p(yp), _p(y), B, Cout, T, 0, _stream())
-        ctx.save_for_backward(v, g, x_btc, wbwd, inv)
+        ctx.save_for_backward(v, g, x_wg, wbwd, inv)
         ctx.cfg = (B, Cin, Cout, T)
         ctx.link = link if (fuse_bwd and link is not None and link.C == Cin) else None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        v, g, x_btc, wbwd, inv = ctx.saved_tensors
+        v, g, x_wg, wbwd, inv = ctx.saved_tensors
         B, Cin, Cout, T = ctx.cfg
         dy = _c(dy)
         dev, bf = dy.device, torch.bfloat16
         K2p = _pad8(2 * Cout)
         dyp = torch.empty(B, 2 * Cout, T, device=dev)
         lib.call("dv3_interleave2", _p(dy), _p(dyp), B, Cout, T, 1, _stream())
-        g_btc = torch.empty(2, B, T, K2p, device=dev, dtype=torch.float16)
+        g_btc = torch.empty(2, B, T, K2p, device=dev, dtype=bf)
         db2 = torch.zeros(2 * Cout, device=dev)
         lib.call("dv3_tc_grad_split", _p(dyp), None, _p(g_btc), None, _p(db2), B, 2 * Cout, T, 0, _stream())
         dbias = db2[:Cout] + db2[Cout:]
@@ -717,7 +728,7 @@ class _ConvT2TCFn(torch.autograd.Function):
             numel = v.numel()
             partials = torch.empty(nsplit, numel, device=dev)
             # element (m=(j,co), ci) -> v layout (ci, co, j): ci*2*Cout + co*2 + j
-            lib.call("dv3_tc_wgrad_mn", _p(g_btc), _p(x_btc), _p(partials), numel, B, M, Cin, T, 1, 1, 0, Cout, 2, 1,
+            lib.call("dv3_tc_wgrad_mn", _p(g_btc), _p(x_wg), _p(partials), numel, B, M, Cin, T, 1, 1, 0, Cout, 2, 1,
                      2 * Cout, 0, _stream())
             dv, dg = _wn_bwd(partials, nsplit, v, g, inv)
         return dx, dv, dg, dbias, None, None

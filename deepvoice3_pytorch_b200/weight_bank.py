@@ -43,7 +43,7 @@ class _Layer:
         self.inv = torch.empty(Cout, device=dev)
         self.scale = torch.empty(Cout, device=dev)
         self.wfwd = torch.empty(2, k, Cout, _pad8(Cin), device=dev, dtype=torch.float16)
-        self.wbwd = torch.empty(2, k, Cin, _pad8(Cout), device=dev, dtype=torch.float16)
+        self.wbwd = torch.empty(2, k, Cin, _pad8(Cout), device=dev, dtype=bf)
         self.partials = None
         self.nsplit = 0
         self.prepared = False

@@ -179,12 +179,12 @@ int dv3_deemphasis(const float* x, float* y, int nclips, int n_samples, long lon
  * pitches are padded to a multiple of 8.  Callers use the exact-fp32 entry points for unsupported shapes. */
 int dv3_tc_supported(int B, int C, int T, int k);           /* gated block: C % 128 == 0, k <= 8 */
 int dv3_tc_conv_supported(int B, int Cin, int Cout, int T, int k);   /* plain conv: k == 1 or Cout % 128 == 0 */
-/* Operand planes: every fp32 operand x travels as an fp16 pair hi = rn16(x), lo = rn16((x - hi) * 2^11)
- * (csrc/common.cuh): 22-bit operands, fp32-class products.  Gradient planes (dv3_tc_gate_bwd_split, dv3_tc_grad_split,
- * Dv3TcFuse.post_planes) hold the gradient times 2^10 so that 1e-9 .. 1e-2 magnitudes sit in the fp16 range; the
- * data-gradient / weight-gradient epilogues multiply by 2^-10.
- * x (B,C,T) fp32 -> conv-input dropout -> btc: [2][B][T][Cp] (Cp = pad8(C)): operand of the forward GEMM and of the
- * weight gradient.  npl must be 2, bct NULL. */
+/* Operand planes: every fp32 operand x travels as hi = rn16(x), lo = rn16((x - hi) * 2^11) (csrc/common.cuh).
+ * Forward GEMMs multiply fp16 pairs (22-bit operands: fp32-class results; activations and normalised weights are O(1),
+ * values are clamped to +-65504); gradient GEMMs multiply bf16 pairs (gradients need the fp32 exponent range for any
+ * loss scale) -- tcgen05 kind::f16 does not mix formats in one MMA, so a conv input is split into both.
+ * x (B,C,T) fp32 -> conv-input dropout -> btc: [2][B][T][Cp] fp16 pair (forward operand, Cp = pad8(C)) and
+ * bct (may be NULL): [2][B][T][Cp] bf16 pair of the same values (operand of the weight gradient). npl must be 2. */
 int dv3_tc_split_input(const float* x, void* btc, int npl, void* bct, int B, int C, int T, int k, int dilation,
                        int causal, float p_drop, const unsigned long long* seed_ptr, unsigned salt, void* stream);
 /* gate backward writing dAB = [da ; db] as planes btc: [2][B][T][2C] (dgrad operand), bct: [2][B][2C][T] (wgrad). */
@@ -220,7 +220,8 @@ int dv3_weightnorm_bwd_batched(const Dv3WnEntry* table_dev, int n, int bwd_block
 /* Work the GEMM epilogues can fuse for the neighbouring ops (NULL = none):
  *  - forward (dv3_tc_convblock_fwd, dv3_tc_conv): np != NULL -> also write the operand planes [2][B][T][np_pitch] of
  *    out * dropmask(np_p, np_seed, np_salt), i.e. what dv3_tc_split_input would produce for the CONSUMER conv
- *    (np_pitch = pad8(channels of this call's output));
+ *    (np_pitch = pad8(channels of this call's output)): np = the fp16 pair its forward GEMM reads, np_wg = the bf16
+ *    pair its weight gradient reads (NULL when the consumer needs no weight gradient);
  *  - data gradient (dv3_tc_conv with transpose_taps = 1): post_kind != 0 -> the tensor this call writes is
  *    dL/d(output of a producer op); apply that producer's backward and emit ITS gradient planes + bias-gradient sums:
  *      1 GLU gate, 2 highway gate: post_a / post_s = the producer's saved a, s (post_x = its input, highway only),
@@ -228,7 +229,7 @@ int dv3_weightnorm_bwd_batched(const Dv3WnEntry* table_dev, int n, int bwd_block
  *      3 ReLU (post_a = the producer's output), 4 identity: planes [2][B][T][pad8(Nc)], post_dbias[Nc] += sums
  *    (what dv3_tc_gate_bwd_split / dv3_tc_grad_split would produce from this call's output). */
 typedef struct Dv3TcFuse {
-    void* np; const unsigned long long* np_seed; float np_p; unsigned np_salt; int np_pitch;
+    void* np; void* np_wg; const unsigned long long* np_seed; float np_p; unsigned np_salt; int np_pitch;
     int post_kind, post_residual;
     const float* post_a; const float* post_s; const float* post_x;
     void* post_planes; float* post_dbias;
