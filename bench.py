@@ -488,15 +488,15 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": frames * args.steps / t_res, "unit": "mel-frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_res / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"tc": "f32 via split-fp16 pairs (3 fp16 tcgen05 MMA passes per product, fp32 accumulate)",
+        "dtype": {"tc": "f32 via split 16-bit pairs (fp16 pairs forward, bf16 pairs for gradients; 3 tcgen05 MMA passes per product, fp32 accumulate)",
                   "bf16x3": "as tc", "fp32": "f32"}[args.math], "data": "synthetic",
         "config": {"workload": WORKLOAD % args.preset + ", random-init weights, fwd+losses+bwd+clip+Adam",
                    "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "inputs larger than L2 (>1.5 GB touched per step)",
                    "cuda_graph": not args.no_graph, "conv_math": args.math,
-                   "conv_math_note": {"tc": "tcgen05: every fp32 operand as an fp16 (hi, lo*2^11) pair = 22-bit operands, "
-                                            "hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (gradient operands "
-                                            "pre-scaled by 2^10); all three presets within rtol 1e-3 / atol 1e-4 of the "
+                   "conv_math_note": {"tc": "tcgen05: forward operands as fp16 (hi, lo*2^11) pairs = 22-bit operands, "
+                                            "gradient GEMMs on bf16 pairs (16 bits, full fp32 range), hi*hi + hi*lo + lo*hi "
+                                            "with fp32 accumulation in TMEM; all three presets within rtol 1e-3 / atol 1e-4 of the "
                                             "fp32 oracle at B=16, full depth (tests/test_gpu_models.py)",
                                       "bf16x3": "alias of tc",
                                       "fp32": "exact fp32 FMA on CUDA cores"}[args.math]},

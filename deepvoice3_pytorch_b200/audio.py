@@ -96,8 +96,8 @@ def stft_mel_batch(wav, lengths=None, want_linear=True, want_mel=True):
     lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
     max_frames = num_frames(max_len)
     basis, start, length = _device_basis(dev)
-    lin = torch.zeros(nclips, max_frames, hparams.fft_size // 2 + 1, device=dev) if want_linear else None
-    mel = torch.zeros(nclips, max_frames, hparams.num_mels, device=dev) if want_mel else None
+    lin = torch.empty(nclips, max_frames, hparams.fft_size // 2 + 1, device=dev) if want_linear else None
+    mel = torch.empty(nclips, max_frames, hparams.num_mels, device=dev) if want_mel else None   # kernel zero-fills ragged tails
 
     def p(t):
         return None if t is None else ctypes.c_void_p(t.data_ptr())

@@ -1,19 +1,33 @@
 // Fused audio front-end: preemphasis -> sqrt-Hann STFT (1024 / hop 256, 768-sample zero padding on both sides)
 // -> |.| -> { linear: dB, normalise } and { mel filterbank -> dB, normalise } in ONE pass over the waveform.
 // Replaces reference audio.py:31-34 (spectrogram) and :46-51 (melspectrogram), which run TWO independent lws
-// STFTs per clip on the CPU (ljspeech.py:63-67).  HBM/PCIe-bound by construction (32 FLOP/B): each 1024-sample
-// frame is read once from L2-resident waveform, transformed in shared memory, and only the (513 + n_mels) floats the
-// trainer stores per frame are written back.
+// STFTs per clip on the CPU (ljspeech.py:63-67).  HBM-bound by construction (about 32 FLOP/B): every sample is read
+// once, and only the (513 + n_mels) floats the trainer stores per frame are written back.
 //
-// One CTA (256 threads) per frame.  Real-input trick: 1024 real samples -> 512-point complex radix-2 FFT in shared
-// memory (one butterfly per thread per stage) -> split into the 513-bin half spectrum.
+// Work decomposition: one CTA (8 warps) walks 32 consecutive frames of one clip, 8 at a time -- ONE WARP PER FRAME.
+//   * the 11*256 raw samples the 8 frames overlap on are staged once in shared memory by cp.async (zero-filled
+//     outside the clip), the copy for the next 8 frames in flight while the mel rows of the current ones are formed;
+//   * each warp runs the register-resident radix-8 transform of stft_core.cuh (pre-emphasis and window applied as
+//     the points are read; 16 complex points per lane, two exchanges through its private work area, __syncwarp only),
+//     splits it into the 513-bin half spectrum two bins at a time, writes the normalised dB row straight from the
+//     split and leaves the magnitudes in shared memory;
+//   * the mel rows are sparse (mel_start / mel_len): the non-zero weights are packed into shared memory once per CTA
+//     and every warp forms its share of the filters for all 8 frames at once (lane = frame x 4 bin phases, bank-
+//     conflict free because consecutive frames' planes are 4 banks apart);
+//   * window, twiddles and split factors are built once per CTA (tables in shared memory), dB through lg2.approx.
+// Frames beyond a clip's own count (ragged batches) are zero-filled by the kernel, so callers pass uninitialised
+// output buffers.
 #include "common.cuh"
+#include "stft_core.cuh"
 
 namespace dv3 {
 
-constexpr int FFT_N = 1024, HOP = 256, NH = 512, NBINS = 513, PAD = FFT_N - HOP;
+using namespace stftc;
 
-__device__ __forceinline__ int bitrev9(int x) { return (int)(__brev((unsigned)x) >> 23); }
+constexpr int FFT_N = 1024, HOP = 256, NH = 512, NBINS = 513, PAD = FFT_N - HOP;
+constexpr int STFT_WARPS = 8, STFT_GROUPS = 4, STFT_FRAMES = STFT_WARPS * STFT_GROUPS;     // frames per CTA
+constexpr int STAGE_N = (STFT_WARPS + 3) * HOP;                                            // samples 8 frames span
+constexpr int MAX_MELS = 128;
 
 struct StftParams {
     const float* wav;          // (nclips, max_len)
@@ -27,93 +41,180 @@ struct StftParams {
     float preemph, min_level_db, ref_level_db;
 };
 
-__device__ __forceinline__ float amp_to_norm_db(float v, float min_level, float min_db, float ref_db) {
-    const float s = 20.f * log10f(fmaxf(min_level, v)) - ref_db;     // audio.py:79-81, :33/:49
-    return fminf(fmaxf((s - min_db) / -min_db, 0.f), 1.f);            // audio.py:88-89
+constexpr int MEL_NNZ = 2048;           // packed non-zero mel weights kept in shared memory (680 for the presets)
+
+struct StftSmem {
+    float raw[STAGE_N + 4];               // raw[2 + i] = x[s0 + i], raw[1] = x[s0 - 1]: raw samples of the 8-frame group
+    f2 win[NH];                           // (w[2n], w[2n+1])
+    f2 tw1[7 * 64];                       // W512^(t*k0)
+    f2 tw2[7 * 8];                        // W64^(n0*k1)
+    f2 wsp[NH / 2 + 2];                   // W1024^k, k <= 256
+    int2 melseg[MAX_MELS];                // (start, len) of every mel row
+    int meloff[MAX_MELS + 1];             // offset of the row's weights in wt[]
+    float wt[MEL_NNZ];
+    float work[STFT_WARPS][2][WORK];      // per-warp re / im planes; the magnitudes end up in plane 0
+};
+static_assert((2 * WORK) % 32 == 4, "frame planes must sit 4 banks apart for the mel stage");
+
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// raw samples x[s0-1 .. s0+STAGE_N) of the clip -> sm.raw[1 ..], zero outside [0, len)
+__device__ __forceinline__ void stage_async(float* raw, const float* x, int s0, int len, int tid) {
+    for (int i = tid; i < STAGE_N + 1; i += STFT_WARPS * 32) {
+        const int s = s0 - 1 + i;
+        const bool ok = s >= 0 && s < len;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(raw + 1 + i);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(x + (ok ? s : 0)), "r"(ok ? 4 : 0)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(256) stft_mel_kernel(const __grid_constant__ StftParams p) {
+__global__ void __launch_bounds__(STFT_WARPS * 32, 3) stft_mel_kernel(const __grid_constant__ StftParams p) {
     pdl_trigger(); pdl_wait();     // programmatic dependent launch: see common.cuh
-    __shared__ float zr[NH], zi[NH];
-    __shared__ float twr[NH / 2], twi[NH / 2];
-    __shared__ float mag[NBINS + 3];
-    const int clip = blockIdx.y, frame = blockIdx.x, tid = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StftSmem& sm = *reinterpret_cast<StftSmem*>(smem_raw);
+    const int clip = blockIdx.y, f_begin = blockIdx.x * STFT_FRAMES, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int len = p.lengths[clip];
-    const int nframes = (len + 2 * PAD - FFT_N + HOP - 1) / HOP + 1;       // ceil((len+2*768-1024)/256)+1
-    if (frame >= nframes) return;
-    const float* x = p.wav + (size_t)clip * p.max_len;
+    const int nframes = min((len + 2 * PAD - FFT_N + HOP - 1) / HOP + 1, p.max_frames);   // ceil((len+2*768-1024)/256)+1
+    const int f_end = min(f_begin + STFT_FRAMES, p.max_frames);
 
-    // twiddles W512^j = exp(-2*pi*i*j/512), j < 256
+    // frames of this chunk past the clip's own end: zero-fill (contiguous rows)
     {
-        float s, c;
-        sincospif(-(float)tid / 256.f, &s, &c);
-        twr[tid] = c; twi[tid] = s;
+        const int z0 = max(f_begin, nframes);
+        if (z0 < f_end) {
+            const size_t row0 = (size_t)clip * p.max_frames + z0;
+            if (p.linear) {
+                float* o = p.linear + row0 * NBINS;
+                for (int i = tid; i < (f_end - z0) * NBINS; i += blockDim.x) o[i] = 0.f;
+            }
+            if (p.mel) {
+                float* o = p.mel + row0 * p.n_mels;
+                for (int i = tid; i < (f_end - z0) * p.n_mels; i += blockDim.x) o[i] = 0.f;
+            }
+        }
     }
-    // load: z[n] = w[2n]*xe[2n] + i*w[2n+1]*xe[2n+1] into bit-reversed position; thread handles n = tid, tid+256
-    const int base = frame * HOP - PAD;
-    const float wscale = 2.f * HOP / FFT_N;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int n = tid + h * 256;
-        float v[2];
+    if (f_begin >= nframes) return;
+
+    const float* x = p.wav + (size_t)clip * p.max_len;
+    stage_async(sm.raw, x, f_begin * HOP - PAD, len, tid);          // in flight while the tables are built
+
+    // ---- tables, once per CTA ----
+    for (int n = tid; n < NH; n += blockDim.x) {
+        float w[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int i = 2 * n + e, s = base + i;
-            float xe = 0.f;
-            if (s >= 0 && s < len) xe = x[s] - (s > 0 ? p.preemph * x[s - 1] : 0.f);
+            const int i = 2 * n + e;
             const float hann = 0.5f - 0.5f * cospif((2 * i + 1) / (float)FFT_N);   // 0.5*(1-cos(2*pi*(i+.5)/N))
-            v[e] = xe * sqrtf(hann * wscale);
+            w[e] = sqrtf(hann * (2.f * HOP / FFT_N));
         }
-        const int r = bitrev9(n);
-        zr[r] = v[0]; zi[r] = v[1];
+        sm.win[n] = {w[0], w[1]};
     }
-    __syncthreads();
-    // 9 radix-2 DIT stages, one butterfly per thread
-#pragma unroll
-    for (int s = 0; s < 9; ++s) {
-        const int half = 1 << s;
-        const int pos = tid & (half - 1);
-        const int i0 = ((tid >> s) << (s + 1)) + pos, i1 = i0 + half;
-        const int tw = pos << (8 - s);
-        const float wr = twr[tw], wi = twi[tw];
-        const float ar = zr[i0], ai = zi[i0], br0 = zr[i1], bi0 = zi[i1];
-        const float br = br0 * wr - bi0 * wi, bi = br0 * wi + bi0 * wr;
-        zr[i0] = ar + br; zi[i0] = ai + bi;
-        zr[i1] = ar - br; zi[i1] = ai - bi;
-        __syncthreads();
+    for (int i = tid; i < 7 * 64; i += blockDim.x) {
+        const int k0 = i / 64 + 1, t = i & 63;
+        float s, c; sincospif(-(float)(t * k0) / 256.f, &s, &c);
+        sm.tw1[i] = {c, s};
     }
-    // split: X[k] = E + W1024^k * O,  E = (Z[k]+conj(Z[N-k]))/2,  O = -i*(Z[k]-conj(Z[N-k]))/2
-    for (int k = tid; k <= NH; k += 256) {
-        const int ka = k & (NH - 1), kb = (NH - k) & (NH - 1);
-        const float ar = zr[ka], ai = zi[ka], br = zr[kb], bi = -zi[kb];
-        const float er = 0.5f * (ar + br), ei = 0.5f * (ai + bi);
-        const float dr = 0.5f * (ar - br), di = 0.5f * (ai - bi);
-        const float orr = di, oi = -dr;                                  // -i * (dr + i di)
-        float s, c;
-        sincospif(-(float)k / 512.f, &s, &c);
-        const float xr = er + c * orr - s * oi, xi = ei + c * oi + s * orr;
-        mag[k] = sqrtf(xr * xr + xi * xi);
+    if (tid < 7 * 8) {
+        const int k1 = tid / 8 + 1, n0 = tid & 7;
+        float s, c; sincospif(-(float)(n0 * k1) / 32.f, &s, &c);
+        sm.tw2[tid] = {c, s};
     }
-    __syncthreads();
-    const float min_level = expf(p.min_level_db / 20.f * 2.302585092994046f);
-    const size_t fidx = (size_t)clip * p.max_frames + frame;
-    if (p.linear) {
-        float* out = p.linear + fidx * NBINS;
-        for (int k = tid; k < NBINS; k += 256)
-            out[k] = amp_to_norm_db(mag[k], min_level, p.min_level_db, p.ref_level_db);
+    for (int k = tid; k <= NH / 2; k += blockDim.x) {
+        float s, c; sincospif(-(float)k / 512.f, &s, &c);
+        sm.wsp[k] = {c, s};
     }
     if (p.mel) {
-        const int warp = tid >> 5, lane = tid & 31;
-        float* out = p.mel + fidx * p.n_mels;
-        for (int m = warp; m < p.n_mels; m += 8) {
-            const int st = p.mel_start[m], ln = p.mel_len[m];
-            const float* row = p.mel_basis + (size_t)m * NBINS + st;
-            float acc = 0.f;
-            for (int j = lane; j < ln; j += 32) acc = fmaf(row[j], mag[st + j], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) out[m] = amp_to_norm_db(acc, min_level, p.min_level_db, p.ref_level_db);
+        for (int m = tid; m < p.n_mels; m += blockDim.x) sm.melseg[m] = make_int2(p.mel_start[m], p.mel_len[m]);
+        if (tid == 0) {
+            int off = 0;
+            for (int m = 0; m < p.n_mels; ++m) { sm.meloff[m] = off; off += p.mel_len[m]; }
+            sm.meloff[p.n_mels] = off;
         }
     }
+    __syncthreads();
+    const bool packed = p.mel && sm.meloff[p.n_mels] <= MEL_NNZ;    // else the weights stay in global memory
+    if (packed)
+        for (int m = warp; m < p.n_mels; m += STFT_WARPS) {
+            const int2 seg = sm.melseg[m];
+            const float* row = p.mel_basis + (size_t)m * NBINS + seg.x;
+            for (int j = lane; j < seg.y; j += 32) sm.wt[sm.meloff[m] + j] = row[j];
+        }
+
+    // normalised dB: clip((20*log10(max(min_level, v)) - ref - min_db) / -min_db, 0, 1)   (audio.py:79-81, :88-89)
+    //   = sat(c2 * log2(max(min_level, v)) + c0);  on p4 = |2X|^2: log2(v) = log2(p4)/2 - 1
+    const float inv = 1.f / -p.min_level_db;
+    const float c2 = 6.020599913279624f * inv, c0 = 1.f - p.ref_level_db * inv;
+    const float min_level = exp2f(p.min_level_db * 0.16609640474436813f);        // 10^(min_db/20)
+    const float c2h = 0.5f * c2, c0l = c0 - c2, min_p4 = 4.f * min_level * min_level;
+
+    float* re = sm.work[warp][0];
+    float* im = sm.work[warp][1];
+
+    for (int g = 0; g < STFT_GROUPS; ++g) {
+        const int f0 = f_begin + g * STFT_WARPS;
+        if (f0 >= nframes) break;                                   // uniform over the CTA
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                            // raw[] landed; the previous group's mel stage is done
+        const int frame = f0 + warp;
+        const size_t fidx = (size_t)clip * p.max_frames + frame;
+        if (frame < nframes) {                                      // warp-uniform
+            cpx v[2][8];
+            pass1(lane, sm.raw + 2 + warp * HOP, p.preemph, len - (frame * HOP - PAD), sm.win, sm.tw1, v);
+            store1(lane, v, re, im);
+            __syncwarp();
+            pass2(lane, re, im, sm.tw2, v);
+            __syncwarp();
+            store2(lane, v, re, im);
+            __syncwarp();
+            pass3(lane, re, im, v);
+            __syncwarp();
+            store3(lane, v, re, im);
+            __syncwarp();
+
+            // split into the half spectrum: bins (k, 512-k), k = lane + 32*j; dB row out, magnitudes back into re[]
+            float* lin = p.linear ? p.linear + fidx * NBINS : nullptr;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const int k = lane + 32 * j;
+                if (k <= NH / 2) {
+                    float plo, phi;
+                    split_pair(k, re, im, sm.wsp[k], plo, phi);
+                    if (lin) {
+                        lin[k] = __saturatef(fmaf(c2h, lg2_approx(fmaxf(plo, min_p4)), c0l));
+                        if (k != NH / 2) lin[NH - k] = __saturatef(fmaf(c2h, lg2_approx(fmaxf(phi, min_p4)), c0l));
+                    }
+                    // every index is read by exactly one lane (its own pair), so overwriting in place is safe
+                    re[k] = 0.5f * sqrt_approx(plo);
+                    if (k != NH / 2) re[NH - k] = 0.5f * sqrt_approx(phi);
+                }
+            }
+        }
+        __syncthreads();                                            // all 8 frames' magnitudes are in place; raw[] is free
+        if (g + 1 < STFT_GROUPS && f0 + STFT_WARPS < nframes)
+            stage_async(sm.raw, x, (f0 + STFT_WARPS) * HOP - PAD, len, tid);
+
+        if (p.mel) {
+            // lane = 4*frame + phase: the 4 phases of a frame stride a filter's bins, all 8 frames in one go
+            const int fl = lane >> 2, q = lane & 3;
+            const float* magf = sm.work[fl][0];
+            const bool fvalid = f0 + fl < nframes;
+            float* out = p.mel + ((size_t)clip * p.max_frames + f0 + fl) * p.n_mels;
+            for (int m = warp; m < p.n_mels; m += STFT_WARPS) {
+                const int2 seg = sm.melseg[m];
+                const float* w = packed ? sm.wt + sm.meloff[m] : p.mel_basis + (size_t)m * NBINS + seg.x;
+                const float* mg = magf + seg.x;
+                float acc = 0.f;
+                for (int jj = q; jj < seg.y; jj += 4) acc = fmaf(w[jj], mg[jj], acc);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                if (q == 0 && fvalid) out[m] = __saturatef(fmaf(c2, lg2_approx(fmaxf(acc, min_level)), c0));
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace dv3
@@ -129,10 +230,15 @@ int dv3_stft_mel(const float* wav, const int* lengths, const float* mel_basis, c
                  const int* mel_len, float* linear, float* mel, int nclips, int max_len, int max_frames,
                  int n_mels, float preemph, float min_level_db, float ref_level_db, void* stream) {
     DV3_REQUIRE(nclips >= 1 && nclips <= 65535, "stft_mel: nclips %d out of range", nclips);
-    DV3_REQUIRE(max_frames >= dv3_stft_num_frames(max_len) || max_frames > 0, "stft_mel: bad max_frames");
+    DV3_REQUIRE(max_frames >= 1, "stft_mel: bad max_frames %d", max_frames);
+    DV3_REQUIRE(n_mels >= 0 && n_mels <= MAX_MELS, "stft_mel: n_mels %d > %d", n_mels, MAX_MELS);
     StftParams p = {wav, lengths, mel_basis, mel_start, mel_len, linear, mel, max_len, max_frames, n_mels,
                     preemph, min_level_db, ref_level_db};
-    launch_k(stft_mel_kernel, dim3(max_frames, nclips), 256, 0, (cudaStream_t)stream, p);
+    static const cudaError_t attr = cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)sizeof(StftSmem));
+    DV3_REQUIRE(attr == cudaSuccess, "stft_mel: cannot reserve %zu bytes of shared memory", sizeof(StftSmem));
+    launch_k(stft_mel_kernel, dim3((max_frames + STFT_FRAMES - 1) / STFT_FRAMES, nclips), STFT_WARPS * 32,
+             sizeof(StftSmem), (cudaStream_t)stream, p);
     return check_launch("stft_mel");
 }
 

@@ -152,7 +152,8 @@ int dv3_adam_clip(float* p, const float* g, float* m, float* v, long long n, con
  * (:64-68), dB (:79-81) and normalisation (:88-89).  wav (nclips, max_len) fp32; lengths int32 [nclips];
  * mel_basis (n_mels, 513) dense with mel_start/mel_len [n_mels] giving each filter's non-zero span;
  * linear (nclips, max_frames, 513) and mel (nclips, max_frames, n_mels) -- the transposed (T, F) layout the
- * preprocessors store (ljspeech.py:72-73); either output may be NULL.  Frames >= a clip's own count are untouched. */
+ * preprocessors store (ljspeech.py:72-73); either output may be NULL.  Frames >= a clip's own count are zero-filled (outputs need no
+ * initialisation); n_mels <= 128. */
 int dv3_stft_num_frames(int n_samples);
 int dv3_stft_mel(const float* wav, const int* lengths, const float* mel_basis, const int* mel_start,
                  const int* mel_len, float* linear, float* mel, int nclips, int max_len, int max_frames,
