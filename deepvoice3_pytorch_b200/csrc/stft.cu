@@ -5,16 +5,19 @@
 // once, and only the (513 + n_mels) floats the trainer stores per frame are written back.
 //
 // Work decomposition: one CTA (8 warps) walks 32 consecutive frames of one clip, 8 at a time -- ONE WARP PER FRAME.
-//   * the 11*256 raw samples the 8 frames overlap on are staged once in shared memory by cp.async (zero-filled
+//   * the 11*256 raw samples the 8 frames overlap on are staged once in shared memory by 16-byte cp.async (zero-filled
 //     outside the clip), the copy for the next 8 frames in flight while the mel rows of the current ones are formed;
-//   * each warp runs the register-resident radix-8 transform of stft_core.cuh (pre-emphasis and window applied as
-//     the points are read; 16 complex points per lane, two exchanges through its private work area, __syncwarp only),
-//     splits it into the 513-bin half spectrum two bins at a time, writes the normalised dB row straight from the
-//     split and leaves the magnitudes in shared memory;
-//   * the mel rows are sparse (mel_start / mel_len): the non-zero weights are packed into shared memory once per CTA
-//     and every warp forms its share of the filters for all 8 frames at once (lane = frame x 4 bin phases, bank-
-//     conflict free because consecutive frames' planes are 4 banks apart);
-//   * window, twiddles and split factors are built once per CTA (tables in shared memory), dB through lg2.approx.
+//   * each warp runs the register-resident radix-8 transform of stft_core.cuh: two butterflies per lane held as
+//     register PAIRS, all arithmetic as packed f32x2 instructions (FADD2 / FMUL2 / FFMA2), pre-emphasis and window
+//     applied as the points are read, two exchanges through its private work area (__syncwarp only), then the split
+//     into the 513-bin half spectrum four bins at a time; the normalised dB row goes straight to global memory
+//     (coalesced) and the magnitudes stay in shared memory;
+//   * the mel rows are sparse (mel_start / mel_len): once per CTA the non-zero weights are packed per QUAD of filters
+//     (rows aligned to 4 bins, zero-padded to the quad's longest row); lane = (frame, filter of the quad) then runs
+//     pure 128-bit loads + FMAs over all 8 frames at once (conflict-free because consecutive frames' planes are an odd
+//     number of 16-byte words apart).  Filterbanks that do not fit the packed form take a plain (slow) loop;
+//   * window, twiddles and split factors come from one table built once per device in double precision (init kernel),
+//     copied into shared memory per CTA; dB through lg2.approx.
 // Frames beyond a clip's own count (ragged batches) are zero-filled by the kernel, so callers pass uninitialised
 // output buffers.
 #include "common.cuh"
@@ -27,7 +30,9 @@ using namespace stftc;
 constexpr int FFT_N = 1024, HOP = 256, NH = 512, NBINS = 513, PAD = FFT_N - HOP;
 constexpr int STFT_WARPS = 8, STFT_GROUPS = 4, STFT_FRAMES = STFT_WARPS * STFT_GROUPS;     // frames per CTA
 constexpr int STAGE_N = (STFT_WARPS + 3) * HOP;                                            // samples 8 frames span
-constexpr int MAX_MELS = 128;
+constexpr int MAX_MELS = 128, MAX_QUADS = MAX_MELS / 4;
+constexpr int MEL_NNZ = 2048;           // packed (zero-padded) mel weights kept in shared memory (1.1 k for the presets)
+constexpr int MEL_REACH = 568;          // a packed row may read magnitude-plane words below this index (all written)
 
 struct StftParams {
     const float* wav;          // (nclips, max_len)
@@ -39,34 +44,55 @@ struct StftParams {
     float* mel;                // (nclips, max_frames, n_mels) or null
     int max_len, max_frames, n_mels;
     float preemph, min_level_db, ref_level_db;
+    int aligned16;             // every clip starts on a 16-byte boundary: 16-byte staging copies
 };
 
-constexpr int MEL_NNZ = 2048;           // packed non-zero mel weights kept in shared memory (680 for the presets)
+__device__ f4 g_stft_tab[TAB_N];        // window / twiddle tables, see stft_core.cuh
+
+__global__ void stft_tables_kernel() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < TAB_N) g_stft_tab[i] = table_entry(i);
+}
 
 struct StftSmem {
-    float raw[STAGE_N + 4];               // raw[2 + i] = x[s0 + i], raw[1] = x[s0 - 1]: raw samples of the 8-frame group
-    f2 win[NH];                           // (w[2n], w[2n+1])
-    f2 tw1[7 * 64];                       // W512^(t*k0)
-    f2 tw2[7 * 8];                        // W64^(n0*k1)
-    f2 wsp[NH / 2 + 2];                   // W1024^k, k <= 256
-    int2 melseg[MAX_MELS];                // (start, len) of every mel row
-    int meloff[MAX_MELS + 1];             // offset of the row's weights in wt[]
-    float wt[MEL_NNZ];
-    float work[STFT_WARPS][2][WORK];      // per-warp re / im planes; the magnitudes end up in plane 0
+    alignas(16) float raw[STAGE_N + 8];   // raw[4 + i] = x[s0 + i] (16-byte aligned frames), raw[3] = x[s0 - 1]
+    f4 tab[TAB_N];
+    alignas(16) float wt[MEL_NNZ];        // packed mel weights: quad Q at qoff[Q], row q at + q*L4, zero padded
+    int start4[MAX_MELS];                 // first bin of the row, rounded down to a multiple of 4
+    int pre[MAX_MELS];                    // zero weights in front of the row (start - start4)
+    int len[MAX_MELS];
+    int start[MAX_MELS];
+    int qL4[MAX_QUADS];                   // padded row length of the quad (multiple of 4)
+    int qoff[MAX_QUADS];
+    int badw[4];                          // per warp of the set-up: a row of its filters reaches past MEL_REACH
+    int packed;                           // 1: every quad fits the packed form
+    alignas(16) float work[STFT_WARPS][2][WORK];      // per-warp re / im planes; the magnitudes end up in plane 0
 };
-static_assert((2 * WORK) % 32 == 4, "frame planes must sit 4 banks apart for the mel stage");
+static_assert((2 * WORK) % 4 == 0 && ((2 * WORK) / 4) % 2 == 1, "frame planes must sit an odd number of 16-byte words apart");
+static_assert((WORK * 4) % 8 == 0, "the im plane must be 8-byte aligned");
 
-__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// raw samples x[s0-1 .. s0+STAGE_N) of the clip -> sm.raw[1 ..], zero outside [0, len)
+// raw samples x[s0-4 .. s0+STAGE_N) of the clip -> sm.raw[0 ..], zero outside [0, len)
+template <bool A16>
 __device__ __forceinline__ void stage_async(float* raw, const float* x, int s0, int len, int tid) {
-    for (int i = tid; i < STAGE_N + 1; i += STFT_WARPS * 32) {
-        const int s = s0 - 1 + i;
-        const bool ok = s >= 0 && s < len;
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(raw + 1 + i);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(x + (ok ? s : 0)), "r"(ok ? 4 : 0)
-                     : "memory");
+    if (A16) {
+        for (int i = tid; i < (STAGE_N + 4) / 4; i += STFT_WARPS * 32) {
+            const int s = s0 - 4 + 4 * i;                        // multiple of 4: a piece never straddles sample 0
+            const int nb = s < 0 ? 0 : min(max(len - s, 0), 4) * 4;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(raw + 4 * i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(x + (nb ? s : 0)), "r"(nb)
+                         : "memory");
+        }
+    } else {
+        for (int i = tid; i < STAGE_N + 1; i += STFT_WARPS * 32) {
+            const int s = s0 - 1 + i;
+            const bool ok = s >= 0 && s < len;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(raw + 3 + i);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(x + (ok ? s : 0)), "r"(ok ? 4 : 0)
+                         : "memory");
+        }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -99,48 +125,52 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 3) stft_mel_kernel(const __gr
     if (f_begin >= nframes) return;
 
     const float* x = p.wav + (size_t)clip * p.max_len;
-    stage_async(sm.raw, x, f_begin * HOP - PAD, len, tid);          // in flight while the tables are built
+    const bool a16 = p.aligned16 != 0;
+    if (a16) stage_async<true>(sm.raw, x, f_begin * HOP - PAD, len, tid);      // in flight while the tables are set up
+    else stage_async<false>(sm.raw, x, f_begin * HOP - PAD, len, tid);
 
     // ---- tables, once per CTA ----
-    for (int n = tid; n < NH; n += blockDim.x) {
-        float w[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int i = 2 * n + e;
-            const float hann = 0.5f - 0.5f * cospif((2 * i + 1) / (float)FFT_N);   // 0.5*(1-cos(2*pi*(i+.5)/N))
-            w[e] = sqrtf(hann * (2.f * HOP / FFT_N));
-        }
-        sm.win[n] = {w[0], w[1]};
-    }
-    for (int i = tid; i < 7 * 64; i += blockDim.x) {
-        const int k0 = i / 64 + 1, t = i & 63;
-        float s, c; sincospif(-(float)(t * k0) / 256.f, &s, &c);
-        sm.tw1[i] = {c, s};
-    }
-    if (tid < 7 * 8) {
-        const int k1 = tid / 8 + 1, n0 = tid & 7;
-        float s, c; sincospif(-(float)(n0 * k1) / 32.f, &s, &c);
-        sm.tw2[tid] = {c, s};
-    }
-    for (int k = tid; k <= NH / 2; k += blockDim.x) {
-        float s, c; sincospif(-(float)k / 512.f, &s, &c);
-        sm.wsp[k] = {c, s};
-    }
-    if (p.mel) {
-        for (int m = tid; m < p.n_mels; m += blockDim.x) sm.melseg[m] = make_int2(p.mel_start[m], p.mel_len[m]);
-        if (tid == 0) {
-            int off = 0;
-            for (int m = 0; m < p.n_mels; ++m) { sm.meloff[m] = off; off += p.mel_len[m]; }
-            sm.meloff[p.n_mels] = off;
-        }
+    for (int i = tid; i < TAB_N; i += blockDim.x) sm.tab[i] = g_stft_tab[i];
+    const int nquads = (p.n_mels + 3) >> 2;
+    if (p.mel && tid < MAX_MELS) {                 // warps 0-3: one thread per filter, a quad = 4 consecutive lanes
+        const int m = tid;
+        const int s = m < p.n_mels ? p.mel_start[m] : 0, l = m < p.n_mels ? p.mel_len[m] : 0;
+        const int s4 = s & ~3, ext = l > 0 ? (s - s4) + l : 0;
+        int mx = max(ext, __shfl_xor_sync(0xffffffffu, ext, 1));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const int L4 = (mx + 3) & ~3;
+        sm.start4[m] = s4; sm.pre[m] = s - s4; sm.len[m] = l; sm.start[m] = s;
+        if ((m & 3) == 0) sm.qL4[m >> 2] = L4;
+        const bool bad = l > 0 && s4 + L4 > MEL_REACH;
+        const bool anybad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) sm.badw[warp] = anybad;
     }
     __syncthreads();
-    const bool packed = p.mel && sm.meloff[p.n_mels] <= MEL_NNZ;    // else the weights stay in global memory
+    if (p.mel && warp == 0) {                      // exclusive scan of the quads' packed sizes
+        const int sz = lane < nquads ? 4 * sm.qL4[lane] : 0;
+        int inc = sz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        sm.qoff[lane] = inc - sz;
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane == 0) sm.packed = (!(sm.badw[0] | sm.badw[1] | sm.badw[2] | sm.badw[3]) && total <= MEL_NNZ) ? 1 : 0;
+    }
+    __syncthreads();
+    const bool packed = p.mel && sm.packed == 1;
     if (packed)
-        for (int m = warp; m < p.n_mels; m += STFT_WARPS) {
-            const int2 seg = sm.melseg[m];
-            const float* row = p.mel_basis + (size_t)m * NBINS + seg.x;
-            for (int j = lane; j < seg.y; j += 32) sm.wt[sm.meloff[m] + j] = row[j];
+        for (int Q = warp; Q < nquads; Q += STFT_WARPS) {
+            const int L4 = sm.qL4[Q], off = sm.qoff[Q];
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                const int m = 4 * Q + q, pre = sm.pre[m], l = sm.len[m];
+                const float* row = p.mel_basis + (size_t)m * NBINS + sm.start[m] - pre;
+#pragma unroll 1
+                for (int jj = lane; jj < L4; jj += 32)
+                    sm.wt[off + q * L4 + jj] = (jj >= pre && jj - pre < l) ? row[jj] : 0.f;
+            }
         }
 
     // normalised dB: clip((20*log10(max(min_level, v)) - ref - min_db) / -min_db, 0, 1)   (audio.py:79-81, :88-89)
@@ -152,6 +182,7 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 3) stft_mel_kernel(const __gr
 
     float* re = sm.work[warp][0];
     float* im = sm.work[warp][1];
+    const f4 *win = sm.tab + TAB_WIN, *tw1 = sm.tab + TAB_TW1, *tw2 = sm.tab + TAB_TW2, *wsp = sm.tab + TAB_WSP;
 
     for (int g = 0; g < STFT_GROUPS; ++g) {
         const int f0 = f_begin + g * STFT_WARPS;
@@ -161,56 +192,79 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 3) stft_mel_kernel(const __gr
         const int frame = f0 + warp;
         const size_t fidx = (size_t)clip * p.max_frames + frame;
         if (frame < nframes) {                                      // warp-uniform
-            cpx v[2][8];
-            pass1(lane, sm.raw + 2 + warp * HOP, p.preemph, len - (frame * HOP - PAD), sm.win, sm.tw1, v);
-            store1(lane, v, re, im);
+            pr vr[8], vi[8];
+            const int lim = len - (frame * HOP - PAD);              // samples of the frame before the clip's end
+            const float* xs = sm.raw + 4 + warp * HOP;
+            if (lim < FFT_N) pass1<true>(lane, xs, p.preemph, lim, win, tw1, vr, vi);     // warp-uniform
+            else pass1<false>(lane, xs, p.preemph, lim, win, tw1, vr, vi);
+            store1(lane, vr, vi, re, im);
             __syncwarp();
-            pass2(lane, re, im, sm.tw2, v);
+            pass2(lane, re, im, tw2, vr, vi);
             __syncwarp();
-            store2(lane, v, re, im);
+            store2(lane, vr, vi, re, im);
             __syncwarp();
-            pass3(lane, re, im, v);
+            pass3(lane, re, im, vr, vi);
             __syncwarp();
-            store3(lane, v, re, im);
+            store3(lane, vr, vi, re, im);
             __syncwarp();
 
-            // split into the half spectrum: bins (k, 512-k), k = lane + 32*j; dB row out, magnitudes back into re[]
+            // split into the half spectrum, bins (k, k+32, 512-k, 480-k), k = lane + 64*j; dB row out, magnitudes back
+            // into re[] (every index is read and written by exactly one lane in one step, so in place is safe)
             float* lin = p.linear ? p.linear + fidx * NBINS : nullptr;
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                const int k = lane + 32 * j;
-                if (k <= NH / 2) {
-                    float plo, phi;
-                    split_pair(k, re, im, sm.wsp[k], plo, phi);
-                    if (lin) {
-                        lin[k] = __saturatef(fmaf(c2h, lg2_approx(fmaxf(plo, min_p4)), c0l));
-                        if (k != NH / 2) lin[NH - k] = __saturatef(fmaf(c2h, lg2_approx(fmaxf(phi, min_p4)), c0l));
-                    }
-                    // every index is read by exactly one lane (its own pair), so overwriting in place is safe
-                    re[k] = 0.5f * sqrt_approx(plo);
-                    if (k != NH / 2) re[NH - k] = 0.5f * sqrt_approx(phi);
+            for (int j = 0; j < 4; ++j) {
+                const int ka = lane + 64 * j;
+                pr lo, hi;
+                split4(ka, re, im, wsp[j * 32 + lane], lo, hi);
+                if (lin) {
+                    lin[ka] = __saturatef(fmaf(c2h, lg2_approx(fmaxf(lo.x, min_p4)), c0l));
+                    lin[ka + 32] = __saturatef(fmaf(c2h, lg2_approx(fmaxf(lo.y, min_p4)), c0l));
+                    lin[NH - ka] = __saturatef(fmaf(c2h, lg2_approx(fmaxf(hi.x, min_p4)), c0l));
+                    lin[NH - 32 - ka] = __saturatef(fmaf(c2h, lg2_approx(fmaxf(hi.y, min_p4)), c0l));
                 }
+                re[ka] = 0.5f * sqrt_approx(lo.x);
+                re[ka + 32] = 0.5f * sqrt_approx(lo.y);
+                re[NH - ka] = 0.5f * sqrt_approx(hi.x);
+                re[NH - 32 - ka] = 0.5f * sqrt_approx(hi.y);
+            }
+            if (lane == 0) {
+                const float pn = split_nyquist(re, im);
+                if (lin) lin[NH / 2] = __saturatef(fmaf(c2h, lg2_approx(fmaxf(pn, min_p4)), c0l));
+                re[NH / 2] = 0.5f * sqrt_approx(pn);
             }
         }
         __syncthreads();                                            // all 8 frames' magnitudes are in place; raw[] is free
-        if (g + 1 < STFT_GROUPS && f0 + STFT_WARPS < nframes)
-            stage_async(sm.raw, x, (f0 + STFT_WARPS) * HOP - PAD, len, tid);
+        if (g + 1 < STFT_GROUPS && f0 + STFT_WARPS < nframes) {
+            if (a16) stage_async<true>(sm.raw, x, (f0 + STFT_WARPS) * HOP - PAD, len, tid);
+            else stage_async<false>(sm.raw, x, (f0 + STFT_WARPS) * HOP - PAD, len, tid);
+        }
 
         if (p.mel) {
-            // lane = 4*frame + phase: the 4 phases of a frame stride a filter's bins, all 8 frames in one go
-            const int fl = lane >> 2, q = lane & 3;
+            // lane = (frame fl, filter q of the quad): all 8 frames of the group in one go
+            const int fl = lane & 7, q = lane >> 3;
             const float* magf = sm.work[fl][0];
             const bool fvalid = f0 + fl < nframes;
             float* out = p.mel + ((size_t)clip * p.max_frames + f0 + fl) * p.n_mels;
-            for (int m = warp; m < p.n_mels; m += STFT_WARPS) {
-                const int2 seg = sm.melseg[m];
-                const float* w = packed ? sm.wt + sm.meloff[m] : p.mel_basis + (size_t)m * NBINS + seg.x;
-                const float* mg = magf + seg.x;
+            for (int Q = warp; Q < nquads; Q += STFT_WARPS) {
+                const int m = 4 * Q + q;
                 float acc = 0.f;
-                for (int jj = q; jj < seg.y; jj += 4) acc = fmaf(w[jj], mg[jj], acc);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                if (q == 0 && fvalid) out[m] = __saturatef(fmaf(c2, lg2_approx(fmaxf(acc, min_level)), c0));
+                if (packed) {
+                    const int L4 = sm.qL4[Q];
+                    const f4* w4 = reinterpret_cast<const f4*>(sm.wt + sm.qoff[Q] + q * L4);
+                    const f4* m4 = reinterpret_cast<const f4*>(magf + sm.start4[m]);
+#pragma unroll 2
+                    for (int jj = 0; jj < (L4 >> 2); ++jj) {
+                        const f4 a = m4[jj], b = w4[jj];
+                        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
+                        acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+                    }
+                } else if (m < p.n_mels) {                           // general filterbank: weights from global memory
+                    const int s = sm.start[m], l = sm.len[m];
+                    const float* w = p.mel_basis + (size_t)m * NBINS + s;
+#pragma unroll 1
+                    for (int jj = 0; jj < l; ++jj) acc = fmaf(w[jj], magf[s + jj], acc);
+                }
+                if (fvalid && m < p.n_mels) out[m] = __saturatef(fmaf(c2, lg2_approx(fmaxf(acc, min_level)), c0));
             }
         }
     }
@@ -226,14 +280,34 @@ extern "C" {
 // frames produced for a clip of n samples: ceil((n + 2*768 - 1024)/256) + 1   (lws "perfectrec" padding)
 int dv3_stft_num_frames(int n_samples) { return (n_samples + 2 * PAD - FFT_N + HOP - 1) / HOP + 1; }
 
+// The table kernel runs once per device (synchronously, so that other streams may use the table afterwards); inside a
+// stream capture it is simply recorded in front of every STFT launch (it is idempotent).
+static int stft_tables(cudaStream_t st) {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
+    if (done[dev]) return 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    stft_tables_kernel<<<(TAB_N + 127) / 128, 128, 0, st>>>();
+    if (cudaGetLastError() != cudaSuccess) return 1;
+    if (cap == cudaStreamCaptureStatusNone) {
+        if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+        done[dev] = true;
+    }
+    return 0;
+}
+
 int dv3_stft_mel(const float* wav, const int* lengths, const float* mel_basis, const int* mel_start,
                  const int* mel_len, float* linear, float* mel, int nclips, int max_len, int max_frames,
                  int n_mels, float preemph, float min_level_db, float ref_level_db, void* stream) {
     DV3_REQUIRE(nclips >= 1 && nclips <= 65535, "stft_mel: nclips %d out of range", nclips);
     DV3_REQUIRE(max_frames >= 1, "stft_mel: bad max_frames %d", max_frames);
     DV3_REQUIRE(n_mels >= 0 && n_mels <= MAX_MELS, "stft_mel: n_mels %d > %d", n_mels, MAX_MELS);
+    DV3_REQUIRE(stft_tables((cudaStream_t)stream) == 0, "stft_mel: cannot build the transform tables");
+    const int aligned16 = (reinterpret_cast<uintptr_t>(wav) % 16 == 0) && (max_len % 4 == 0);
     StftParams p = {wav, lengths, mel_basis, mel_start, mel_len, linear, mel, max_len, max_frames, n_mels,
-                    preemph, min_level_db, ref_level_db};
+                    preemph, min_level_db, ref_level_db, aligned16};
     static const cudaError_t attr = cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)sizeof(StftSmem));
     DV3_REQUIRE(attr == cudaSuccess, "stft_mel: cannot reserve %zu bytes of shared memory", sizeof(StftSmem));

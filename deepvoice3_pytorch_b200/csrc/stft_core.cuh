@@ -2,17 +2,22 @@
 // (tests/test_stft_core.py runs the stages lane by lane on the CPU and compares with numpy's rfft).
 //
 // One warp transforms one frame.  1024 real samples are packed as 512 complex points z[n] = x[2n] + i*x[2n+1];
-// the 512-point transform is three radix-8 passes (512 = 8*8*8) with the 16 points of a lane held in registers
-// (two "virtual threads" t = lane + 32*h of 8 points each) and two exchanges through the warp's shared-memory
-// work area -- __syncwarp only, no block barrier.  With n = 64*n2 + 8*n1 + n0 and k = k0 + 8*k1 + 64*k2:
-//   pass 1  thread t = 8*n1 + n0 : A[k0]  = W512^(t*k0)  * sum_n2 z[64*n2 + t]      * W8^(n2*k0)
-//   pass 2  thread (k0, n0)      : B[k1]  = W64^(n0*k1)  * sum_n1 A[k0][8*n1 + n0]  * W8^(n1*k1)
-//   pass 3  thread (k0, k1)      : Z[k]   =                sum_n0 B[k0][k1][n0]     * W8^(n0*k2)
-// Exchange layouts are chosen so that every warp-wide access hits 32 distinct banks:
-//   exchange 1  addr = 72*k0 + t                 written t-contiguous, read by lanes (k0 = lane/8 + 4h, n0 = lane%8)
-//   exchange 2  addr = k0 + 8*k1 + 68*n0         written by those lanes, read by lanes (k0 = lane%8, k1 = lane/8 + 4h)
-//   natural     addr = k                         written by those lanes (k mod 32 = k0 + 8*(k1%4)), read contiguously
-// The half spectrum follows from Z by the usual even/odd split, two bins (k, 512-k) per step.
+// the 512-point transform is three radix-8 passes (512 = 8*8*8).  Every lane runs TWO butterflies per pass ("virtual
+// threads" a and b) and keeps their data as PAIRS pr = (value of a, value of b): all arithmetic is pair-wise, which
+// on sm_100 is one FADD2 / FMUL2 / FFMA2 (add/mul/fma.f32x2) per pair -- half the issue slots of scalar code.  The
+// pairing of every pass is chosen so that the loads deliver pairs in adjacent registers (64/128-bit shared-memory
+// accesses) with no register shuffling.  With n = 64*n2 + 8*n1 + n0 and k = k0 + 8*k1 + 64*k2:
+//   pass 1  lane l: a,b = points t = 2l, 2l+1   A[k0]  = W512^(t*k0) * sum_n2 z[64*n2 + t]      * W8^(n2*k0)
+//   pass 2  lane l = 4*k0 + m: a,b = n0 = 2m, 2m+1
+//                                                 B[k1]  = W64^(n0*k1) * sum_n1 A[k0][8*n1 + n0]  * W8^(n1*k1)
+//   pass 3  lane l = 4*k1 + u: a,b = k0 = 2u, 2u+1
+//                                                 Z[k]   =               sum_n0 B[k0][k1][n0]     * W8^(n0*k2)
+// Exchanges through the warp's work area (re / im planes of WORK floats, viewed as pairs):
+//   exchange 1  pair (A[k0][2l], A[k0][2l+1]) at pair index 36*k0 + l     64-bit stores, 64-bit loads at 36*k0 + 4*n1 + m
+//   exchange 2  B[k0][k1][n0] at float index 68*n0 + 8*k1 + k0            32-bit stores, 64-bit loads at pair 34*n0 + l
+//   natural     pair (Z[2l + 64*k2], Z[2l + 1 + 64*k2]) at pair index l + 32*k2
+// (row pitches 36 / 34 pairs make every warp-wide access conflict-free.)  The half spectrum follows from Z by the usual
+// even/odd split, here four bins per step: k_a = lane + 64*j, k_b = k_a + 32 and their mirrors 512 - k.
 #pragma once
 #if defined(__CUDACC__)
 #define STFT_HD __host__ __device__ __forceinline__
@@ -24,128 +29,217 @@
 namespace dv3 {
 namespace stftc {
 
-struct cpx { float r, i; };
 struct f2 { float x, y; };
+struct alignas(16) f4 { float x, y, z, w; };
+typedef f2 pr;                   // (virtual thread a, virtual thread b)
 
-constexpr int WORK = 578;        // floats per plane (re / im) of a warp's work area; 2*WORK = 4 (mod 32), see stft.cu
-constexpr int PITCH1 = 72;       // exchange 1 row pitch
-constexpr int PITCH2 = 68;       // exchange 2 n0 pitch
+constexpr int WORK = 578;        // floats per plane (re / im) of a warp's work area; 2*WORK/4 is odd, see stft.cu
+constexpr int PITCH1 = 36;       // exchange 1: pairs per k0 row
+constexpr int PITCH2 = 34;       // exchange 2: pairs per n0 row
 
-STFT_HD cpx cadd(cpx a, cpx b) { return {a.r + b.r, a.i + b.i}; }
-STFT_HD cpx csub(cpx a, cpx b) { return {a.r - b.r, a.i - b.i}; }
-STFT_HD cpx cmul(cpx a, f2 w) { return {a.r * w.x - a.i * w.y, a.r * w.y + a.i * w.x}; }
+// ---- pair arithmetic: one instruction per pair on the device ----------------------------------------------------
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned long long pk_(pr a) {
+    unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r;
+}
+__device__ __forceinline__ pr upk_(unsigned long long v) {
+    pr a; asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(v)); return a;
+}
+__device__ __forceinline__ pr padd(pr a, pr b) {
+    unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk_(a)), "l"(pk_(b))); return upk_(r);
+}
+__device__ __forceinline__ pr psub(pr a, pr b) {
+    unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk_(a)), "l"(pk_(b))); return upk_(r);
+}
+__device__ __forceinline__ pr pmul(pr a, pr b) {
+    unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk_(a)), "l"(pk_(b))); return upk_(r);
+}
+__device__ __forceinline__ pr pfma(pr a, pr b, pr c) {          // a*b + c
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk_(a)), "l"(pk_(b)), "l"(pk_(c)));
+    return upk_(r);
+}
+__device__ __forceinline__ pr pfnma(pr a, pr b, pr c) {         // c - a*b  (the negation folds into the FFMA2 operand)
+    return pfma(pr{-a.x, -a.y}, b, c);
+}
+#else
+STFT_HD pr padd(pr a, pr b) { return {a.x + b.x, a.y + b.y}; }
+STFT_HD pr psub(pr a, pr b) { return {a.x - b.x, a.y - b.y}; }
+STFT_HD pr pmul(pr a, pr b) { return {a.x * b.x, a.y * b.y}; }
+STFT_HD pr pfma(pr a, pr b, pr c) { return {fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+STFT_HD pr pfnma(pr a, pr b, pr c) { return {fmaf(-a.x, b.x, c.x), fmaf(-a.y, b.y, c.y)}; }
+#endif
 
-// in-place 8-point forward DFT: a[k] <- sum_n a[n] * exp(-2*pi*i*n*k/8)
-STFT_HD void radix8(cpx* a) {
-    const float h = 0.70710678118654752f;
-    const cpx b0 = cadd(a[0], a[4]), b1 = csub(a[0], a[4]), b2 = cadd(a[2], a[6]), b3 = csub(a[2], a[6]);
-    const cpx b4 = cadd(a[1], a[5]), b5 = csub(a[1], a[5]), b6 = cadd(a[3], a[7]), b7 = csub(a[3], a[7]);
-    const cpx e0 = cadd(b0, b2), e2 = csub(b0, b2);
-    const cpx e1 = {b1.r + b3.i, b1.i - b3.r}, e3 = {b1.r - b3.i, b1.i + b3.r};          // b1 -/+ i*b3
-    const cpx o0 = cadd(b4, b6), o2 = csub(b4, b6);
-    const cpx o1 = {b5.r + b7.i, b5.i - b7.r}, o3 = {b5.r - b7.i, b5.i + b7.r};
-    const cpx t1 = {h * (o1.r + o1.i), h * (o1.i - o1.r)};                               // (1-i)/sqrt2 * o1
-    const cpx t2 = {o2.i, -o2.r};                                                        // -i * o2
-    const cpx t3 = {h * (o3.i - o3.r), -h * (o3.r + o3.i)};                              // (-1-i)/sqrt2 * o3
-    a[0] = cadd(e0, o0); a[4] = csub(e0, o0);
-    a[1] = cadd(e1, t1); a[5] = csub(e1, t1);
-    a[2] = cadd(e2, t2); a[6] = csub(e2, t2);
-    a[3] = cadd(e3, t3); a[7] = csub(e3, t3);
+// (r, i) <- (r, i) * (wx + i*wy), pair-wise
+STFT_HD void cmulp(pr& r, pr& i, pr wx, pr wy) {
+    const pr nr = pfnma(i, wy, pmul(r, wx));
+    const pr ni = pfma(i, wx, pmul(r, wy));
+    r = nr; i = ni;
 }
 
-// pass 1: x -> sample 0 of the frame window in the RAW waveform (x[-1] is readable; samples outside the clip are 0);
-// pre-emphasis e[i] = x[i] - c*x[i-1] (audio.py:21-23) is applied on the fly and e[i] = 0 for i >= lim (the padding
-// after the clip's last sample); win[n] = (w[2n], w[2n+1]), tw1[(k0-1)*64 + t] = W512^(t*k0)
-STFT_HD void pass1(int lane, const float* x, float preemph, int lim, const f2* win, const f2* tw1, cpx (&v)[2][8]) {
-    const f2* xz = reinterpret_cast<const f2*>(x);
+// in-place 8-point forward DFT of two butterflies at once: a[k] <- sum_n a[n] * exp(-2*pi*i*n*k/8)
+STFT_HD void radix8p(pr* r, pr* i) {
+    const pr hh = {0.70710678118654752f, 0.70710678118654752f};
+    const pr b0r = padd(r[0], r[4]), b0i = padd(i[0], i[4]), b1r = psub(r[0], r[4]), b1i = psub(i[0], i[4]);
+    const pr b2r = padd(r[2], r[6]), b2i = padd(i[2], i[6]), b3r = psub(r[2], r[6]), b3i = psub(i[2], i[6]);
+    const pr b4r = padd(r[1], r[5]), b4i = padd(i[1], i[5]), b5r = psub(r[1], r[5]), b5i = psub(i[1], i[5]);
+    const pr b6r = padd(r[3], r[7]), b6i = padd(i[3], i[7]), b7r = psub(r[3], r[7]), b7i = psub(i[3], i[7]);
+    const pr e0r = padd(b0r, b2r), e0i = padd(b0i, b2i), e2r = psub(b0r, b2r), e2i = psub(b0i, b2i);
+    const pr e1r = padd(b1r, b3i), e1i = psub(b1i, b3r), e3r = psub(b1r, b3i), e3i = padd(b1i, b3r);   // b1 -/+ i*b3
+    const pr o0r = padd(b4r, b6r), o0i = padd(b4i, b6i), o2r = psub(b4r, b6r), o2i = psub(b4i, b6i);
+    const pr o1r = padd(b5r, b7i), o1i = psub(b5i, b7r), o3r = psub(b5r, b7i), o3i = padd(b5i, b7r);
+    const pr s1 = padd(o1r, o1i), d1 = psub(o1i, o1r);       // (1-i)/sqrt2 * o1 = h*(s1, d1)
+    const pr s3 = padd(o3r, o3i), d3 = psub(o3i, o3r);       // (-1-i)/sqrt2 * o3 = h*(d3, -s3)
+    r[0] = padd(e0r, o0r); i[0] = padd(e0i, o0i); r[4] = psub(e0r, o0r); i[4] = psub(e0i, o0i);
+    r[1] = pfma(s1, hh, e1r); i[1] = pfma(d1, hh, e1i); r[5] = pfnma(s1, hh, e1r); i[5] = pfnma(d1, hh, e1i);
+    r[2] = padd(e2r, o2i); i[2] = psub(e2i, o2r); r[6] = psub(e2r, o2i); i[6] = padd(e2i, o2r);       // -i * o2
+    r[3] = pfma(d3, hh, e3r); i[3] = pfnma(s3, hh, e3i); r[7] = pfnma(d3, hh, e3r); i[7] = pfma(s3, hh, e3i);
+}
+
+// ---- tables (built once by stft.cu's init kernel, and by the CPU harness) ----------------------------------------
+//   win [n2*32 + l]     = (w[2n_a], w[2n_b], w[2n_a+1], w[2n_b+1]),  n_a = 64*n2 + 2l, n_b = n_a + 1
+//   tw1 [(k0-1)*32 + l] = (cos a, cos b, sin a, sin b) of W512^(t*k0),  t = 2l, 2l+1
+//   tw2 [(k1-1)*4 + m]  = (cos a, cos b, sin a, sin b) of W64^(n0*k1),  n0 = 2m, 2m+1
+//   wsp [j*32 + l]      = (cos a, cos b, sin a, sin b) of W1024^k,      k = l + 64j, l + 64j + 32
+constexpr int TAB_WIN = 0, TAB_TW1 = 256, TAB_TW2 = TAB_TW1 + 224, TAB_WSP = TAB_TW2 + 28, TAB_N = TAB_WSP + 128;
+
+// cos / sin of -2*pi*num/den in double precision (the init kernel and the CPU harness share table_entry)
+STFT_HD void cs_(int num, int den, float& c, float& s) {
+#if defined(__CUDA_ARCH__)
+    double sd, cd; sincospi(-2.0 * (double)num / (double)den, &sd, &cd);
+#else
+    const double a = -2.0 * 3.14159265358979323846 * (double)num / (double)den, sd = std::sin(a), cd = std::cos(a);
+#endif
+    c = (float)cd; s = (float)sd;
+}
+// frame window: sqrt(hann(i) * 2*hop/N), hann(i) = .5*(1 - cos(2*pi*(i+.5)/N)), N = 1024, hop = 256
+STFT_HD float win_(int i) {
+#if defined(__CUDA_ARCH__)
+    const double h = 0.5 - 0.5 * cospi((2.0 * i + 1.0) / 1024.0);
+    return (float)sqrt(h * 0.5);
+#else
+    const double h = 0.5 - 0.5 * std::cos(3.14159265358979323846 * (2.0 * i + 1.0) / 1024.0);
+    return (float)std::sqrt(h * 0.5);
+#endif
+}
+STFT_HD f4 table_entry(int idx) {
+    f4 r;
+    if (idx < TAB_TW1) {
+        const int n2 = idx >> 5, l = idx & 31, i0 = 128 * n2 + 4 * l;
+        r.x = win_(i0); r.y = win_(i0 + 2); r.z = win_(i0 + 1); r.w = win_(i0 + 3);
+    } else if (idx < TAB_TW2) {
+        const int j = idx - TAB_TW1, k0 = (j >> 5) + 1, l = j & 31;
+        cs_(2 * l * k0, 512, r.x, r.z); cs_((2 * l + 1) * k0, 512, r.y, r.w);
+    } else if (idx < TAB_WSP) {
+        const int j = idx - TAB_TW2, k1 = (j >> 2) + 1, m = j & 3;
+        cs_(2 * m * k1, 64, r.x, r.z); cs_((2 * m + 1) * k1, 64, r.y, r.w);
+    } else {
+        const int j = idx - TAB_WSP, k = (j & 31) + 64 * (j >> 5);
+        cs_(k, 1024, r.x, r.z); cs_(k + 32, 1024, r.y, r.w);
+    }
+    return r;
+}
+
+// pass 1: x -> sample 0 of the frame window in the RAW waveform (16-byte aligned, x[-1] readable; samples outside the
+// clip are 0); pre-emphasis e[i] = x[i] - c*x[i-1] (audio.py:21-23) is applied on the fly.  TAIL: e[i] = 0 for
+// i >= lim (the zero padding after the clip's last sample starts inside this frame).
+template <bool TAIL>
+STFT_HD void pass1(int lane, const float* x, float c, int lim, const f4* win, const f4* tw1, pr (&vr)[8], pr (&vi)[8]) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int t = lane + 32 * h;
-#pragma unroll
-        for (int n2 = 0; n2 < 8; ++n2) {
-            const int n = 64 * n2 + t;
-            const f2 s = xz[n], w = win[n];
-            const float xm = x[2 * n - 1];
-            float e0 = s.x - preemph * xm, e1 = s.y - preemph * s.x;
-            if (lim < 1024) {                                    // warp-uniform: only a clip's last frames
-                if (2 * n >= lim) e0 = 0.f;
-                if (2 * n + 1 >= lim) e1 = 0.f;
-            }
-            v[h][n2] = {e0 * w.x, e1 * w.y};
+    for (int n2 = 0; n2 < 8; ++n2) {
+        const int i0 = 128 * n2 + 4 * lane;                  // first of the 4 samples of points a, b
+        const f4 s = *reinterpret_cast<const f4*>(x + i0);
+        const float xm = x[i0 - 1];
+        const f4 w = win[n2 * 32 + lane];
+        float e0 = fmaf(-c, xm, s.x), e1 = fmaf(-c, s.x, s.y), e2 = fmaf(-c, s.y, s.z), e3 = fmaf(-c, s.z, s.w);
+        if (TAIL) {
+            if (i0 >= lim) e0 = 0.f;
+            if (i0 + 1 >= lim) e1 = 0.f;
+            if (i0 + 2 >= lim) e2 = 0.f;
+            if (i0 + 3 >= lim) e3 = 0.f;
         }
-        radix8(v[h]);
+        vr[n2] = pmul(pr{e0, e2}, pr{w.x, w.y});
+        vi[n2] = pmul(pr{e1, e3}, pr{w.z, w.w});
+    }
+    radix8p(vr, vi);
 #pragma unroll
-        for (int k0 = 1; k0 < 8; ++k0) v[h][k0] = cmul(v[h][k0], tw1[(k0 - 1) * 64 + t]);
+    for (int k0 = 1; k0 < 8; ++k0) {
+        const f4 t = tw1[(k0 - 1) * 32 + lane];
+        cmulp(vr[k0], vi[k0], pr{t.x, t.y}, pr{t.z, t.w});
     }
 }
-STFT_HD void store1(int lane, const cpx (&v)[2][8], float* re, float* im) {
+STFT_HD void store1(int lane, const pr (&vr)[8], const pr (&vi)[8], float* re, float* im) {
+    f2* re2 = reinterpret_cast<f2*>(re);
+    f2* im2 = reinterpret_cast<f2*>(im);
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int k0 = 0; k0 < 8; ++k0) {
-            re[PITCH1 * k0 + lane + 32 * h] = v[h][k0].r;
-            im[PITCH1 * k0 + lane + 32 * h] = v[h][k0].i;
-        }
-}
-// pass 2: tw2[(k1-1)*8 + n0] = W64^(n0*k1)
-STFT_HD void pass2(int lane, const float* re, const float* im, const f2* tw2, cpx (&v)[2][8]) {
-    const int n0 = lane & 7;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int k0 = (lane >> 3) + 4 * h;
-#pragma unroll
-        for (int n1 = 0; n1 < 8; ++n1) v[h][n1] = {re[PITCH1 * k0 + 8 * n1 + n0], im[PITCH1 * k0 + 8 * n1 + n0]};
-        radix8(v[h]);
-#pragma unroll
-        for (int k1 = 1; k1 < 8; ++k1) v[h][k1] = cmul(v[h][k1], tw2[(k1 - 1) * 8 + n0]);
+    for (int k0 = 0; k0 < 8; ++k0) {
+        re2[PITCH1 * k0 + lane] = vr[k0];
+        im2[PITCH1 * k0 + lane] = vi[k0];
     }
 }
-STFT_HD void store2(int lane, const cpx (&v)[2][8], float* re, float* im) {
-    const int n0 = lane & 7;
+STFT_HD void pass2(int lane, const float* re, const float* im, const f4* tw2, pr (&vr)[8], pr (&vi)[8]) {
+    const f2* re2 = reinterpret_cast<const f2*>(re);
+    const f2* im2 = reinterpret_cast<const f2*>(im);
+    const int k0 = lane >> 2, m = lane & 3;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int k0 = (lane >> 3) + 4 * h;
+    for (int n1 = 0; n1 < 8; ++n1) {
+        vr[n1] = re2[PITCH1 * k0 + 4 * n1 + m];
+        vi[n1] = im2[PITCH1 * k0 + 4 * n1 + m];
+    }
+    radix8p(vr, vi);
 #pragma unroll
-        for (int k1 = 0; k1 < 8; ++k1) {
-            re[k0 + 8 * k1 + PITCH2 * n0] = v[h][k1].r;
-            im[k0 + 8 * k1 + PITCH2 * n0] = v[h][k1].i;
-        }
+    for (int k1 = 1; k1 < 8; ++k1) {
+        const f4 t = tw2[(k1 - 1) * 4 + m];
+        cmulp(vr[k1], vi[k1], pr{t.x, t.y}, pr{t.z, t.w});
     }
 }
-STFT_HD void pass3(int lane, const float* re, const float* im, cpx (&v)[2][8]) {
-    const int k0 = lane & 7;
+STFT_HD void store2(int lane, const pr (&vr)[8], const pr (&vi)[8], float* re, float* im) {
+    const int k0 = lane >> 2, m = lane & 3;
+    const int base = 2 * PITCH2 * (2 * m) + k0;              // float index of (n0 = 2m, k1 = 0, k0)
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int k1 = (lane >> 3) + 4 * h;
-#pragma unroll
-        for (int n0 = 0; n0 < 8; ++n0) v[h][n0] = {re[k0 + 8 * k1 + PITCH2 * n0], im[k0 + 8 * k1 + PITCH2 * n0]};
-        radix8(v[h]);
+    for (int k1 = 0; k1 < 8; ++k1) {
+        re[base + 8 * k1] = vr[k1].x;
+        im[base + 8 * k1] = vi[k1].x;
+        re[base + 2 * PITCH2 + 8 * k1] = vr[k1].y;
+        im[base + 2 * PITCH2 + 8 * k1] = vi[k1].y;
     }
 }
-STFT_HD void store3(int lane, const cpx (&v)[2][8], float* re, float* im) {      // natural order Z[k], k < 512
-    const int k0 = lane & 7;
+STFT_HD void pass3(int lane, const float* re, const float* im, pr (&vr)[8], pr (&vi)[8]) {
+    const f2* re2 = reinterpret_cast<const f2*>(re);
+    const f2* im2 = reinterpret_cast<const f2*>(im);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int k1 = (lane >> 3) + 4 * h;
+    for (int n0 = 0; n0 < 8; ++n0) {
+        vr[n0] = re2[PITCH2 * n0 + lane];                    // pair (k0 = 2u, 2u+1) of (k1 = lane>>2, u = lane&3)
+        vi[n0] = im2[PITCH2 * n0 + lane];
+    }
+    radix8p(vr, vi);
+}
+STFT_HD void store3(int lane, const pr (&vr)[8], const pr (&vi)[8], float* re, float* im) {     // natural order Z[k]
+    f2* re2 = reinterpret_cast<f2*>(re);
+    f2* im2 = reinterpret_cast<f2*>(im);
 #pragma unroll
-        for (int k2 = 0; k2 < 8; ++k2) {
-            re[k0 + 8 * k1 + 64 * k2] = v[h][k2].r;
-            im[k0 + 8 * k1 + 64 * k2] = v[h][k2].i;
-        }
+    for (int k2 = 0; k2 < 8; ++k2) {
+        re2[lane + 32 * k2] = vr[k2];
+        im2[lane + 32 * k2] = vi[k2];
     }
 }
-// bins k and 512-k (0 <= k <= 256) from Z[k], Z[512-k]; w = W1024^k.  Returns |2*X[k]|^2 and |2*X[512-k]|^2:
+// bins k_a = lane + 64j, k_b = k_a + 32 (0 <= k < 256) and their mirrors 512 - k from Z[k], Z[512-k]; w = W1024^k.
+// Returns p_lo = (|2X[k_a]|^2, |2X[k_b]|^2) and p_hi = (|2X[512-k_a]|^2, |2X[512-k_b]|^2):
 //   2E = Z[k] + conj(Z[512-k]),  2O = -i*(Z[k] - conj(Z[512-k])),  X[k] = E + w*O,  X[512-k] = conj(E - w*O)
-STFT_HD void split_pair(int k, const float* re, const float* im, f2 w, float& p_lo, float& p_hi) {
-    const int ka = k & 511, kb = (512 - k) & 511;
-    const float ar = re[ka], ai = im[ka], br = re[kb], bi = -im[kb];
-    const float er = ar + br, ei = ai + bi, dr = ar - br, di = ai - bi;
-    const float orr = di, oi = -dr;
-    const float pr = w.x * orr - w.y * oi, pi = w.x * oi + w.y * orr;
-    const float xr = er + pr, xi = ei + pi, yr = er - pr, yi = ei - pi;
-    p_lo = xr * xr + xi * xi;
-    p_hi = yr * yr + yi * yi;
+// (k = 0 pairs Z[0] with itself and yields bins 0 and 512; bin 256 is split_nyquist's.)
+STFT_HD void split4(int ka, const float* re, const float* im, f4 w, pr& p_lo, pr& p_hi) {
+    const int kb = ka + 32, ma = (512 - ka) & 511, mb = 512 - kb;
+    const pr ar = {re[ka], re[kb]}, ai = {im[ka], im[kb]}, br = {re[ma], re[mb]}, bn = {im[ma], im[mb]};
+    const pr er = padd(ar, br), ei = psub(ai, bn), dr = psub(ar, br), di = padd(ai, bn);
+    const pr wx = {w.x, w.y}, wy = {w.z, w.w};
+    const pr p = pfma(wx, di, pmul(wy, dr));                 // Re(w * 2O),  2O = (di, -dr)
+    const pr q = pfnma(wx, dr, pmul(wy, di));                // Im(w * 2O)
+    const pr xr = padd(er, p), xi = padd(ei, q), yr = psub(er, p), yi = psub(ei, q);
+    p_lo = pfma(xr, xr, pmul(xi, xi));
+    p_hi = pfma(yr, yr, pmul(yi, yi));
 }
+// |2X[256]|^2 = 4*|Z[256]|^2   (E = Re Z, O = Im Z, w = -i)
+STFT_HD float split_nyquist(const float* re, const float* im) { return 4.f * (re[256] * re[256] + im[256] * im[256]); }
 
 }  // namespace stftc
 }  // namespace dv3

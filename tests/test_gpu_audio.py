@@ -125,3 +125,47 @@ def test_inv_spectrogram_round_trip_and_oracle():
     got = audio.inv_preemphasis(z).cpu().numpy()
     for i in range(3):
         np.testing.assert_allclose(got[i], A.inv_preemphasis(z[i].cpu().numpy()), rtol=1e-4, atol=1e-4)
+
+
+def test_general_filterbank_and_staging_paths():
+    """(a) A dense 24 x 513 filterbank does not fit the packed per-quad form of the kernel: the plain loop must give
+    basis @ |STFT| like numpy.  (b) The same clips staged through the 16-byte path (row pitch a multiple of 4 samples)
+    and the 4-byte path (odd pitch) give bit-identical outputs."""
+    import ctypes
+    from deepvoice3_pytorch_b200 import audio
+    from deepvoice3_pytorch_b200._lib import lib
+    from oracle import audio_oracle as A
+    rng = np.random.RandomState(7)
+    n = 6000
+    clips = np.stack([A.synthetic_clip(40 + i, n=n) for i in range(3)])
+    T = audio.num_frames(n)
+
+    def run(wav_t, basis, start, length):
+        nm = basis.shape[0]
+        lin = torch.empty(wav_t.shape[0], T, 513, device="cuda")
+        mel = torch.empty(wav_t.shape[0], T, nm, device="cuda")
+        lens = torch.full((wav_t.shape[0],), n, dtype=torch.int32, device="cuda")
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        lib.call("dv3_stft_mel", p(wav_t), p(lens), p(basis), p(start), p(length), p(lin), p(mel), wav_t.shape[0],
+                 wav_t.shape[1], T, nm, 0.97, -100.0, 20.0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        return lin.cpu().numpy(), mel.cpu().numpy()
+
+    # (a) dense filterbank
+    dense = (rng.rand(24, 513).astype(np.float32) + 0.1) / 513.0
+    wav_t = torch.from_numpy(clips).cuda()
+    lin, mel = run(wav_t, torch.from_numpy(dense).cuda(), torch.zeros(24, dtype=torch.int32).cuda(),
+                   torch.full((24,), 513, dtype=torch.int32).cuda())
+    for i in range(3):
+        mag = np.abs(A.lws_stft(A.preemphasis(clips[i].astype(np.float64))))          # (T, 513)
+        ref = A._normalize(A._amp_to_db(mag @ dense.T.astype(np.float64)) - 20.0)
+        assert np.abs(mel[i] - ref).max() < 2e-3
+    # (b) staging paths
+    basis, start, length = audio._device_basis(wav_t.device)
+    lin_a, mel_a = run(wav_t, basis, start, length)                                      # pitch 6000: 16-byte copies
+    wide = torch.zeros(3, n + 1, device="cuda")
+    wide[:, :n] = wav_t
+    lin_b, mel_b = run(wide, basis, start, length)                                       # pitch 6001: 4-byte copies
+    assert np.array_equal(lin_a, lin_b) and np.array_equal(mel_a, mel_b)
+    ref_lin, ref_mel = A.process_utterance(clips[0])
+    _check(lin_a[0], mel_a[0], ref_lin, ref_mel)
