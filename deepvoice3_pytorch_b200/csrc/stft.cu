@@ -20,7 +20,7 @@
 //     copied into shared memory per CTA; dB through lg2.approx.
 // Frames beyond a clip's own count (ragged batches) are zero-filled by the kernel, so callers pass uninitialised
 // output buffers.
-#include "common.cuh"
+#include "tc_common.cuh"
 #include "stft_core.cuh"
 
 namespace dv3 {
@@ -66,6 +66,7 @@ struct StftSmem {
     int qoff[MAX_QUADS];
     int badw[4];                          // per warp of the set-up: a row of its filters reaches past MEL_REACH
     int packed;                           // 1: every quad fits the packed form
+    alignas(8) uint64_t mbar;             // completion of the bulk (TMA) staging copies
     alignas(16) float work[STFT_WARPS][2][WORK];      // per-warp re / im planes; the magnitudes end up in plane 0
 };
 static_assert((2 * WORK) % 4 == 0 && ((2 * WORK) / 4) % 2 == 1, "frame planes must sit an odd number of 16-byte words apart");
@@ -74,10 +75,26 @@ static_assert((WORK * 4) % 8 == 0, "the im plane must be 8-byte aligned");
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// raw samples x[s0-4 .. s0+STAGE_N) of the clip -> sm.raw[0 ..], zero outside [0, len)
-template <bool A16>
-__device__ __forceinline__ void stage_async(float* raw, const float* x, int s0, int len, int tid) {
-    if (A16) {
+// raw samples x[s0-4 .. s0+STAGE_N) of the clip -> sm.raw[0 ..], zero outside [0, len).  Three ways:
+//   BULK   the whole span lies inside the clip and is 16-byte aligned: ONE cp.async.bulk (TMA) issued by thread 0,
+//          completion on sm.mbar -- no LSU instructions or shared-memory wavefronts spent on staging;
+//   A16    16-byte cp.async pieces with zero fill (a clip's first / last groups);
+//   else   4-byte cp.async pieces (rows that do not start on 16-byte boundaries).
+constexpr int STAGE_BYTES = (STAGE_N + 4) * 4;
+static_assert(STAGE_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+__device__ __forceinline__ bool stage_is_bulk(bool a16, int s0, int len) { return a16 && s0 >= 4 && s0 + STAGE_N <= len; }
+__device__ __forceinline__ void stage_async(float* raw, uint64_t* mbar, const float* x, int s0, int len, int tid,
+                                            bool a16) {
+    if (stage_is_bulk(a16, s0, len)) {                         // uniform over the CTA
+        if (tid == 0) {
+            tc::fence_proxy_async();                             // earlier generic-proxy reads of raw[] are ordered by the barrier
+            tc::mbar_arrive_expect_tx(mbar, STAGE_BYTES);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tc::smem_u32(raw)), "l"(x + s0 - 4), "r"(STAGE_BYTES), "r"(tc::smem_u32(mbar)) : "memory");
+        }
+        return;
+    }
+    if (a16) {
         for (int i = tid; i < (STAGE_N + 4) / 4; i += STFT_WARPS * 32) {
             const int s = s0 - 4 + 4 * i;                        // multiple of 4: a piece never straddles sample 0
             const int nb = s < 0 ? 0 : min(max(len - s, 0), 4) * 4;
@@ -126,8 +143,9 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 3) stft_mel_kernel(const __gr
 
     const float* x = p.wav + (size_t)clip * p.max_len;
     const bool a16 = p.aligned16 != 0;
-    if (a16) stage_async<true>(sm.raw, x, f_begin * HOP - PAD, len, tid);      // in flight while the tables are set up
-    else stage_async<false>(sm.raw, x, f_begin * HOP - PAD, len, tid);
+    if (tid == 0) { tc::mbar_init(&sm.mbar, 1); tc::fence_barrier_init(); }   // thread 0 is also the only issuer
+    stage_async(sm.raw, &sm.mbar, x, f_begin * HOP - PAD, len, tid, a16);     // in flight while the tables are set up
+    uint32_t bulk_parity = 0;
 
     // ---- tables, once per CTA ----
     for (int i = tid; i < TAB_N; i += blockDim.x) sm.tab[i] = g_stft_tab[i];
@@ -188,6 +206,7 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 3) stft_mel_kernel(const __gr
         const int f0 = f_begin + g * STFT_WARPS;
         if (f0 >= nframes) break;                                   // uniform over the CTA
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (stage_is_bulk(a16, f0 * HOP - PAD, len)) { tc::mbar_wait(&sm.mbar, bulk_parity); bulk_parity ^= 1; }
         __syncthreads();                                            // raw[] landed; the previous group's mel stage is done
         const int frame = f0 + warp;
         const size_t fidx = (size_t)clip * p.max_frames + frame;
@@ -215,7 +234,7 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 3) stft_mel_kernel(const __gr
             for (int j = 0; j < 4; ++j) {
                 const int ka = lane + 64 * j;
                 pr lo, hi;
-                split4(ka, re, im, wsp[j * 32 + lane], lo, hi);
+                split4(ka, re, im, rot16(wsp[lane], j), lo, hi);
                 if (lin) {
                     lin[ka] = __saturatef(fmaf(c2h, lg2_approx(fmaxf(lo.x, min_p4)), c0l));
                     lin[ka + 32] = __saturatef(fmaf(c2h, lg2_approx(fmaxf(lo.y, min_p4)), c0l));
@@ -234,10 +253,8 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 3) stft_mel_kernel(const __gr
             }
         }
         __syncthreads();                                            // all 8 frames' magnitudes are in place; raw[] is free
-        if (g + 1 < STFT_GROUPS && f0 + STFT_WARPS < nframes) {
-            if (a16) stage_async<true>(sm.raw, x, (f0 + STFT_WARPS) * HOP - PAD, len, tid);
-            else stage_async<false>(sm.raw, x, (f0 + STFT_WARPS) * HOP - PAD, len, tid);
-        }
+        if (g + 1 < STFT_GROUPS && f0 + STFT_WARPS < nframes)
+            stage_async(sm.raw, &sm.mbar, x, (f0 + STFT_WARPS) * HOP - PAD, len, tid, a16);
 
         if (p.mel) {
             // lane = (frame fl, filter q of the quad): all 8 frames of the group in one go

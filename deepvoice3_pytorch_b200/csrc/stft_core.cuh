@@ -97,11 +97,16 @@ STFT_HD void radix8p(pr* r, pr* i) {
 }
 
 // ---- tables (built once by stft.cu's init kernel, and by the CPU harness) ----------------------------------------
-//   win [n2*32 + l]     = (w[2n_a], w[2n_b], w[2n_a+1], w[2n_b+1]),  n_a = 64*n2 + 2l, n_b = n_a + 1
-//   tw1 [(k0-1)*32 + l] = (cos a, cos b, sin a, sin b) of W512^(t*k0),  t = 2l, 2l+1
-//   tw2 [(k1-1)*4 + m]  = (cos a, cos b, sin a, sin b) of W64^(n0*k1),  n0 = 2m, 2m+1
-//   wsp [j*32 + l]      = (cos a, cos b, sin a, sin b) of W1024^k,      k = l + 64j, l + 64j + 32
-constexpr int TAB_WIN = 0, TAB_TW1 = 256, TAB_TW2 = TAB_TW1 + 224, TAB_WSP = TAB_TW2 + 28, TAB_N = TAB_WSP + 128;
+// Only what cannot be formed cheaply in registers is tabulated (the kernel is bound by shared-memory wavefronts, not by
+// arithmetic): the rest follows by angle addition / products of the tabulated factors.
+//   win [l], win[32 + l]  = S*sin(a_j), S*cos(a_j) as (j=0, j=2, j=1, j=3); a_j = pi*(2*(4l+j)+1)/2048, S = sqrt(1/2):
+//                           the frame window is w[i] = S*sin(pi*(2i+1)/2048) (sqrt-Hann * sqrt(2*hop/N)), and sample
+//                           i = 128*n2 + 4l + j sits n2*pi/8 further on: w = S*sin(a_j)*cos(n2*pi/8) + S*cos(a_j)*sin(n2*pi/8)
+//   tw1 [g*32 + l]        = (cos a, cos b, sin a, sin b) of W512^(t*k0),  t = 2l, 2l+1, k0 = 1 (g=0), 4 (g=1);
+//                           k0 = 2, 3, 5, 6, 7 are products of these two (depth <= 3)
+//   tw2 [g*4 + m]         = (cos a, cos b, sin a, sin b) of W64^(n0*k1),  n0 = 2m, 2m+1, k1 = 1, 4; the rest likewise
+//   wsp [l]               = (cos a, cos b, sin a, sin b) of W1024^k,      k = l, l + 32; k + 64j = one rotation by W16^j
+constexpr int TAB_WIN = 0, TAB_TW1 = 64, TAB_TW2 = TAB_TW1 + 64, TAB_WSP = TAB_TW2 + 8, TAB_N = TAB_WSP + 32;
 
 // cos / sin of -2*pi*num/den in double precision (the init kernel and the CPU harness share table_entry)
 STFT_HD void cs_(int num, int den, float& c, float& s) {
@@ -112,32 +117,59 @@ STFT_HD void cs_(int num, int den, float& c, float& s) {
 #endif
     c = (float)cd; s = (float)sd;
 }
-// frame window: sqrt(hann(i) * 2*hop/N), hann(i) = .5*(1 - cos(2*pi*(i+.5)/N)), N = 1024, hop = 256
-STFT_HD float win_(int i) {
+// S*sin / S*cos of pi*(2i+1)/2048, S = sqrt(1/2)
+STFT_HD void wsc_(int i, float& s, float& c) {
 #if defined(__CUDA_ARCH__)
-    const double h = 0.5 - 0.5 * cospi((2.0 * i + 1.0) / 1024.0);
-    return (float)sqrt(h * 0.5);
+    double sd, cd; sincospi((2.0 * i + 1.0) / 2048.0, &sd, &cd);
 #else
-    const double h = 0.5 - 0.5 * std::cos(3.14159265358979323846 * (2.0 * i + 1.0) / 1024.0);
-    return (float)std::sqrt(h * 0.5);
+    const double a = 3.14159265358979323846 * (2.0 * i + 1.0) / 2048.0, sd = std::sin(a), cd = std::cos(a);
 #endif
+    s = (float)(0.70710678118654752440 * sd); c = (float)(0.70710678118654752440 * cd);
 }
 STFT_HD f4 table_entry(int idx) {
     f4 r;
     if (idx < TAB_TW1) {
-        const int n2 = idx >> 5, l = idx & 31, i0 = 128 * n2 + 4 * l;
-        r.x = win_(i0); r.y = win_(i0 + 2); r.z = win_(i0 + 1); r.w = win_(i0 + 3);
+        const int l = idx & 31;
+        float s[4], c[4];
+        for (int j = 0; j < 4; ++j) wsc_(4 * l + j, s[j], c[j]);
+        if (idx < 32) { r.x = s[0]; r.y = s[2]; r.z = s[1]; r.w = s[3]; }
+        else { r.x = c[0]; r.y = c[2]; r.z = c[1]; r.w = c[3]; }
     } else if (idx < TAB_TW2) {
-        const int j = idx - TAB_TW1, k0 = (j >> 5) + 1, l = j & 31;
+        const int j = idx - TAB_TW1, k0 = (j >> 5) ? 4 : 1, l = j & 31;
         cs_(2 * l * k0, 512, r.x, r.z); cs_((2 * l + 1) * k0, 512, r.y, r.w);
     } else if (idx < TAB_WSP) {
-        const int j = idx - TAB_TW2, k1 = (j >> 2) + 1, m = j & 3;
+        const int j = idx - TAB_TW2, k1 = (j >> 2) ? 4 : 1, m = j & 3;
         cs_(2 * m * k1, 64, r.x, r.z); cs_((2 * m + 1) * k1, 64, r.y, r.w);
     } else {
-        const int j = idx - TAB_WSP, k = (j & 31) + 64 * (j >> 5);
-        cs_(k, 1024, r.x, r.z); cs_(k + 32, 1024, r.y, r.w);
+        const int l = idx - TAB_WSP;
+        cs_(l, 1024, r.x, r.z); cs_(l + 32, 1024, r.y, r.w);
     }
     return r;
+}
+
+// twiddle pairs: c = a * b (complex, pair-wise)
+struct tw { pr x, y; };
+STFT_HD tw twmul(tw a, tw b) { return {pfnma(a.y, b.y, pmul(a.x, b.x)), pfma(a.y, b.x, pmul(a.x, b.y))}; }
+// v[1..7] *= w^k given w^1 and w^4 (products of depth <= 3 instead of five more table loads)
+STFT_HD void twiddle7(pr* vr, pr* vi, f4 t1, f4 t4) {
+    const tw w1 = {{t1.x, t1.y}, {t1.z, t1.w}}, w4 = {{t4.x, t4.y}, {t4.z, t4.w}};
+    const tw w2 = twmul(w1, w1), w3 = twmul(w2, w1);
+    cmulp(vr[1], vi[1], w1.x, w1.y);
+    cmulp(vr[2], vi[2], w2.x, w2.y);
+    cmulp(vr[3], vi[3], w3.x, w3.y);
+    cmulp(vr[4], vi[4], w4.x, w4.y);
+    const tw w5 = twmul(w4, w1), w6 = twmul(w4, w2), w7 = twmul(w4, w3);
+    cmulp(vr[5], vi[5], w5.x, w5.y);
+    cmulp(vr[6], vi[6], w6.x, w6.y);
+    cmulp(vr[7], vi[7], w7.x, w7.y);
+}
+// W1024^(k + 64j) = W1024^k * W16^j, j = 1..3 (compile-time constant rotations of the tabulated j = 0 factors)
+STFT_HD f4 rot16(f4 w, int j) {
+    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
+    const float cx = j == 1 ? C1 : (j == 2 ? H : S1), cy = j == 1 ? -S1 : (j == 2 ? -H : -C1);
+    if (j == 0) return w;
+    const tw r = twmul(tw{{w.x, w.y}, {w.z, w.w}}, tw{{cx, cx}, {cy, cy}});
+    return f4{r.x.x, r.x.y, r.y.x, r.y.y};
 }
 
 // pass 1: x -> sample 0 of the frame window in the RAW waveform (16-byte aligned, x[-1] readable; samples outside the
@@ -145,12 +177,21 @@ STFT_HD f4 table_entry(int idx) {
 // i >= lim (the zero padding after the clip's last sample starts inside this frame).
 template <bool TAIL>
 STFT_HD void pass1(int lane, const float* x, float c, int lim, const f4* win, const f4* tw1, pr (&vr)[8], pr (&vi)[8]) {
+    const f4 ws = win[lane], wc = win[32 + lane];
+    const pr sA = {ws.x, ws.y}, sB = {ws.z, ws.w}, cA = {wc.x, wc.y}, cB = {wc.z, wc.w};
+    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
+    const float CB[8] = {1.f, C1, H, S1, 0.f, -S1, -H, -C1}, SB[8] = {0.f, S1, H, C1, 1.f, C1, H, S1};   // n2*pi/8
 #pragma unroll
     for (int n2 = 0; n2 < 8; ++n2) {
         const int i0 = 128 * n2 + 4 * lane;                  // first of the 4 samples of points a, b
         const f4 s = *reinterpret_cast<const f4*>(x + i0);
+#if defined(__CUDA_ARCH__)
+        // x[i0 - 1] is the previous lane's last sample: a shuffle instead of a 4-way conflicting load
+        float xm = __shfl_up_sync(0xffffffffu, s.w, 1);
+        if (lane == 0) xm = x[i0 - 1];
+#else
         const float xm = x[i0 - 1];
-        const f4 w = win[n2 * 32 + lane];
+#endif
         float e0 = fmaf(-c, xm, s.x), e1 = fmaf(-c, s.x, s.y), e2 = fmaf(-c, s.y, s.z), e3 = fmaf(-c, s.z, s.w);
         if (TAIL) {
             if (i0 >= lim) e0 = 0.f;
@@ -158,15 +199,19 @@ STFT_HD void pass1(int lane, const float* x, float c, int lim, const f4* win, co
             if (i0 + 2 >= lim) e2 = 0.f;
             if (i0 + 3 >= lim) e3 = 0.f;
         }
-        vr[n2] = pmul(pr{e0, e2}, pr{w.x, w.y});
-        vi[n2] = pmul(pr{e1, e3}, pr{w.z, w.w});
+        pr wA, wB;                                           // window at samples (i0, i0+2) and (i0+1, i0+3)
+        if (n2 == 0) { wA = sA; wB = sB; }
+        else if (n2 == 4) { wA = cA; wB = cB; }
+        else {
+            const pr cb = {CB[n2], CB[n2]}, sb = {SB[n2], SB[n2]};
+            wA = pfma(cA, sb, pmul(sA, cb));
+            wB = pfma(cB, sb, pmul(sB, cb));
+        }
+        vr[n2] = pmul(pr{e0, e2}, wA);
+        vi[n2] = pmul(pr{e1, e3}, wB);
     }
     radix8p(vr, vi);
-#pragma unroll
-    for (int k0 = 1; k0 < 8; ++k0) {
-        const f4 t = tw1[(k0 - 1) * 32 + lane];
-        cmulp(vr[k0], vi[k0], pr{t.x, t.y}, pr{t.z, t.w});
-    }
+    twiddle7(vr, vi, tw1[lane], tw1[32 + lane]);
 }
 STFT_HD void store1(int lane, const pr (&vr)[8], const pr (&vi)[8], float* re, float* im) {
     f2* re2 = reinterpret_cast<f2*>(re);
@@ -187,11 +232,7 @@ STFT_HD void pass2(int lane, const float* re, const float* im, const f4* tw2, pr
         vi[n1] = im2[PITCH1 * k0 + 4 * n1 + m];
     }
     radix8p(vr, vi);
-#pragma unroll
-    for (int k1 = 1; k1 < 8; ++k1) {
-        const f4 t = tw2[(k1 - 1) * 4 + m];
-        cmulp(vr[k1], vi[k1], pr{t.x, t.y}, pr{t.z, t.w});
-    }
+    twiddle7(vr, vi, tw2[m], tw2[4 + m]);
 }
 STFT_HD void store2(int lane, const pr (&vr)[8], const pr (&vi)[8], float* re, float* im) {
     const int k0 = lane >> 2, m = lane & 3;

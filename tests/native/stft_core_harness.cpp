@@ -38,7 +38,7 @@ int main() {
         for (int l = 0; l < 32; ++l) {
             const int ka = l + 64 * j;
             pr lo, hi;
-            split4(ka, re, im, wsp[j * 32 + l], lo, hi);
+            split4(ka, re, im, rot16(wsp[l], j), lo, hi);
             mag[ka] = 0.5f * std::sqrt(lo.x);
             mag[ka + 32] = 0.5f * std::sqrt(lo.y);
             mag[512 - ka] = 0.5f * std::sqrt(hi.x);
