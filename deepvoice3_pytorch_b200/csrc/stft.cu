@@ -4,7 +4,7 @@
 // STFTs per clip on the CPU (ljspeech.py:63-67).  HBM-bound by construction (about 32 FLOP/B): every sample is read
 // once, and only the (513 + n_mels) floats the trainer stores per frame are written back.
 //
-// Work decomposition: one CTA (8 warps) walks 32 consecutive frames of one clip, 8 at a time -- ONE WARP PER FRAME.
+// Work decomposition: one CTA (8 warps) walks 64 consecutive frames of one clip, 8 at a time -- ONE WARP PER FRAME.
 //   * the 11*256 raw samples the 8 frames overlap on are staged once in shared memory by 16-byte cp.async (zero-filled
 //     outside the clip), the copy for the next 8 frames in flight while the mel rows of the current ones are formed;
 //   * each warp runs the register-resident radix-8 transform of stft_core.cuh: two butterflies per lane held as
@@ -28,7 +28,7 @@ namespace dv3 {
 using namespace stftc;
 
 constexpr int FFT_N = 1024, HOP = 256, NH = 512, NBINS = 513, PAD = FFT_N - HOP;
-constexpr int STFT_WARPS = 8, STFT_GROUPS = 4, STFT_FRAMES = STFT_WARPS * STFT_GROUPS;     // frames per CTA
+constexpr int STFT_WARPS = 8, STFT_GROUPS = 8, STFT_FRAMES = STFT_WARPS * STFT_GROUPS;     // frames per CTA
 constexpr int STAGE_N = (STFT_WARPS + 3) * HOP;                                            // samples 8 frames span
 constexpr int MAX_MELS = 128, MAX_QUADS = MAX_MELS / 4;
 constexpr int MEL_NNZ = 2048;           // packed (zero-padded) mel weights kept in shared memory (1.1 k for the presets)
@@ -43,7 +43,10 @@ struct StftParams {
     float* linear;             // (nclips, max_frames, 513) or null
     float* mel;                // (nclips, max_frames, n_mels) or null
     int max_len, max_frames, n_mels;
-    float preemph, min_level_db, ref_level_db;
+    float preemph;
+    // normalised dB: clip((20*log10(max(min_level, v)) - ref - min_db) / -min_db, 0, 1)   (audio.py:79-81, :88-89)
+    //   = sat(c2 * log2(max(min_level, v)) + c0);  on p4 = |2X|^2 (log2(v) = log2(p4)/2 - 1): sat(c2h * log2(max(min_p4, p4)) + c0l)
+    float c2, c0, min_level, c2h, c0l, min_p4;
     int aligned16;             // every clip starts on a 16-byte boundary: 16-byte staging copies
 };
 
@@ -58,12 +61,8 @@ struct StftSmem {
     alignas(16) float raw[STAGE_N + 8];   // raw[4 + i] = x[s0 + i] (16-byte aligned frames), raw[3] = x[s0 - 1]
     f4 tab[TAB_N];
     alignas(16) float wt[MEL_NNZ];        // packed mel weights: quad Q at qoff[Q], row q at + q*L4, zero padded
-    int start4[MAX_MELS];                 // first bin of the row, rounded down to a multiple of 4
-    int pre[MAX_MELS];                    // zero weights in front of the row (start - start4)
-    int len[MAX_MELS];
-    int start[MAX_MELS];
-    int qL4[MAX_QUADS];                   // padded row length of the quad (multiple of 4)
-    int qoff[MAX_QUADS];
+    int4 frow[MAX_MELS];                  // per filter: (start4 / 4, zero weights in front = start - start4, len, start)
+    int2 qinfo[MAX_QUADS];                // per quad: (offset in wt[] / 4, padded row length / 4)
     int badw[4];                          // per warp of the set-up: a row of its filters reaches past MEL_REACH
     int packed;                           // 1: every quad fits the packed form
     alignas(8) uint64_t mbar;             // completion of the bulk (TMA) staging copies
@@ -150,53 +149,64 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 3) stft_mel_kernel(const __gr
     // ---- tables, once per CTA ----
     for (int i = tid; i < TAB_N; i += blockDim.x) sm.tab[i] = g_stft_tab[i];
     const int nquads = (p.n_mels + 3) >> 2;
+    int myL4 = 0;
     if (p.mel && tid < MAX_MELS) {                 // warps 0-3: one thread per filter, a quad = 4 consecutive lanes
         const int m = tid;
         const int s = m < p.n_mels ? p.mel_start[m] : 0, l = m < p.n_mels ? p.mel_len[m] : 0;
         const int s4 = s & ~3, ext = l > 0 ? (s - s4) + l : 0;
         int mx = max(ext, __shfl_xor_sync(0xffffffffu, ext, 1));
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const int L4 = (mx + 3) & ~3;
-        sm.start4[m] = s4; sm.pre[m] = s - s4; sm.len[m] = l; sm.start[m] = s;
-        if ((m & 3) == 0) sm.qL4[m >> 2] = L4;
-        const bool bad = l > 0 && s4 + L4 > MEL_REACH;
+        myL4 = (mx + 3) & ~3;
+        sm.frow[m] = make_int4(s4 >> 2, s - s4, l, s);
+        if ((m & 3) == 0) sm.qinfo[m >> 2].y = myL4 >> 2;
+        const bool bad = (l > 0 && s4 + myL4 > MEL_REACH) || myL4 > 64;       // the packing below covers 64 columns
         const bool anybad = __any_sync(0xffffffffu, bad);
         if (lane == 0) sm.badw[warp] = anybad;
     }
     __syncthreads();
-    if (p.mel && warp == 0) {                      // exclusive scan of the quads' packed sizes
-        const int sz = lane < nquads ? 4 * sm.qL4[lane] : 0;
+    if (p.mel && warp == 0) {                      // exclusive scan of the quads' packed sizes (in 16-byte words)
+        const int sz = lane < nquads ? 4 * sm.qinfo[lane].y : 0;
         int inc = sz;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += v;
         }
-        sm.qoff[lane] = inc - sz;
+        sm.qinfo[lane].x = inc - sz;
         const int total = __shfl_sync(0xffffffffu, inc, 31);
-        if (lane == 0) sm.packed = (!(sm.badw[0] | sm.badw[1] | sm.badw[2] | sm.badw[3]) && total <= MEL_NNZ) ? 1 : 0;
+        if (lane == 0) sm.packed = (!(sm.badw[0] | sm.badw[1] | sm.badw[2] | sm.badw[3]) && 4 * total <= MEL_NNZ) ? 1 : 0;
     }
     __syncthreads();
     const bool packed = p.mel && sm.packed == 1;
-    if (packed)
-        for (int Q = warp; Q < nquads; Q += STFT_WARPS) {
-            const int L4 = sm.qL4[Q], off = sm.qoff[Q];
-#pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
-                const int m = 4 * Q + q, pre = sm.pre[m], l = sm.len[m];
-                const float* row = p.mel_basis + (size_t)m * NBINS + sm.start[m] - pre;
-#pragma unroll 1
-                for (int jj = lane; jj < L4; jj += 32)
-                    sm.wt[off + q * L4 + jj] = (jj >= pre && jj - pre < l) ? row[jj] : 0.f;
+    if (packed) {
+        // warp w packs rows w, w+8, ...: columns lane and lane+32 of each; four rows' loads are issued before the
+        // first store so that the (L2-latency) loads overlap
+        const int nrows = 4 * nquads;
+        for (int m0 = warp; m0 < nrows; m0 += 4 * STFT_WARPS) {
+            float v[4][2];
+            int dst[4], L4s[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int m = m0 + r * STFT_WARPS;
+                v[r][0] = v[r][1] = 0.f; dst[r] = 0; L4s[r] = 0;
+                if (m < nrows) {
+                    const int4 fr = sm.frow[m];
+                    const int2 qi = sm.qinfo[m >> 2];
+                    L4s[r] = 4 * qi.y; dst[r] = 4 * qi.x + (m & 3) * L4s[r];
+                    const float* row = p.mel_basis + (size_t)m * NBINS + fr.w - fr.y;
+                    const int j0 = lane - fr.y, j1 = lane + 32 - fr.y;
+                    if (j0 >= 0 && j0 < fr.z) v[r][0] = __ldg(row + lane);
+                    if (j1 >= 0 && j1 < fr.z) v[r][1] = __ldg(row + lane + 32);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (lane < L4s[r]) sm.wt[dst[r] + lane] = v[r][0];
+                if (lane + 32 < L4s[r]) sm.wt[dst[r] + lane + 32] = v[r][1];
             }
         }
-
-    // normalised dB: clip((20*log10(max(min_level, v)) - ref - min_db) / -min_db, 0, 1)   (audio.py:79-81, :88-89)
-    //   = sat(c2 * log2(max(min_level, v)) + c0);  on p4 = |2X|^2: log2(v) = log2(p4)/2 - 1
-    const float inv = 1.f / -p.min_level_db;
-    const float c2 = 6.020599913279624f * inv, c0 = 1.f - p.ref_level_db * inv;
-    const float min_level = exp2f(p.min_level_db * 0.16609640474436813f);        // 10^(min_db/20)
-    const float c2h = 0.5f * c2, c0l = c0 - c2, min_p4 = 4.f * min_level * min_level;
+    }
+    const float c2 = p.c2, c0 = p.c0, min_level = p.min_level, c2h = p.c2h, c0l = p.c0l, min_p4 = p.min_p4;
 
     float* re = sm.work[warp][0];
     float* im = sm.work[warp][1];
@@ -257,29 +267,42 @@ __global__ void __launch_bounds__(STFT_WARPS * 32, 3) stft_mel_kernel(const __gr
             stage_async(sm.raw, &sm.mbar, x, (f0 + STFT_WARPS) * HOP - PAD, len, tid, a16);
 
         if (p.mel) {
-            // lane = (frame fl, filter q of the quad): all 8 frames of the group in one go
+            // lane = (frame fl, filter q of the quad): all 8 frames of the group in one go.  Quads are dealt to the
+            // warps longest first in snake order (rows grow with the filter index), so the warps finish together.
             const int fl = lane & 7, q = lane >> 3;
             const float* magf = sm.work[fl][0];
             const bool fvalid = f0 + fl < nframes;
             float* out = p.mel + ((size_t)clip * p.max_frames + f0 + fl) * p.n_mels;
-            for (int Q = warp; Q < nquads; Q += STFT_WARPS) {
-                const int m = 4 * Q + q;
+            for (int k = 0; 8 * k < nquads; ++k) {
+                const int i = 8 * k + ((k & 1) ? STFT_WARPS - 1 - warp : warp);
+                if (i >= nquads) continue;
+                const int Q = nquads - 1 - i, m = 4 * Q + q;
                 float acc = 0.f;
                 if (packed) {
-                    const int L4 = sm.qL4[Q];
-                    const f4* w4 = reinterpret_cast<const f4*>(sm.wt + sm.qoff[Q] + q * L4);
-                    const f4* m4 = reinterpret_cast<const f4*>(magf + sm.start4[m]);
-#pragma unroll 2
-                    for (int jj = 0; jj < (L4 >> 2); ++jj) {
-                        const f4 a = m4[jj], b = w4[jj];
-                        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
-                        acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
-                    }
-                } else if (m < p.n_mels) {                           // general filterbank: weights from global memory
-                    const int s = sm.start[m], l = sm.len[m];
-                    const float* w = p.mel_basis + (size_t)m * NBINS + s;
+                    const int2 qi = sm.qinfo[Q];
+                    const f4* w4 = reinterpret_cast<const f4*>(sm.wt) + qi.x + q * qi.y;
+                    const f4* m4 = reinterpret_cast<const f4*>(magf) + sm.frow[m].x;
+                    float acc1 = 0.f;
+                    int jj = 0;
 #pragma unroll 1
-                    for (int jj = 0; jj < l; ++jj) acc = fmaf(w[jj], magf[s + jj], acc);
+                    for (; jj + 1 < qi.y; jj += 2) {
+                        const f4 a0 = m4[jj], b0 = w4[jj], a1 = m4[jj + 1], b1 = w4[jj + 1];
+                        acc = fmaf(a0.x, b0.x, acc); acc1 = fmaf(a1.x, b1.x, acc1);
+                        acc = fmaf(a0.y, b0.y, acc); acc1 = fmaf(a1.y, b1.y, acc1);
+                        acc = fmaf(a0.z, b0.z, acc); acc1 = fmaf(a1.z, b1.z, acc1);
+                        acc = fmaf(a0.w, b0.w, acc); acc1 = fmaf(a1.w, b1.w, acc1);
+                    }
+                    if (jj < qi.y) {
+                        const f4 a0 = m4[jj], b0 = w4[jj];
+                        acc = fmaf(a0.x, b0.x, acc); acc1 = fmaf(a0.y, b0.y, acc1);
+                        acc = fmaf(a0.z, b0.z, acc); acc1 = fmaf(a0.w, b0.w, acc1);
+                    }
+                    acc += acc1;
+                } else if (m < p.n_mels) {                           // general filterbank: weights from global memory
+                    const int4 fr = sm.frow[m];
+                    const float* w = p.mel_basis + (size_t)m * NBINS + fr.w;
+#pragma unroll 1
+                    for (int jj = 0; jj < fr.z; ++jj) acc = fmaf(w[jj], magf[fr.w + jj], acc);
                 }
                 if (fvalid && m < p.n_mels) out[m] = __saturatef(fmaf(c2, lg2_approx(fmaxf(acc, min_level)), c0));
             }
@@ -323,8 +346,12 @@ int dv3_stft_mel(const float* wav, const int* lengths, const float* mel_basis, c
     DV3_REQUIRE(n_mels >= 0 && n_mels <= MAX_MELS, "stft_mel: n_mels %d > %d", n_mels, MAX_MELS);
     DV3_REQUIRE(stft_tables((cudaStream_t)stream) == 0, "stft_mel: cannot build the transform tables");
     const int aligned16 = (reinterpret_cast<uintptr_t>(wav) % 16 == 0) && (max_len % 4 == 0);
-    StftParams p = {wav, lengths, mel_basis, mel_start, mel_len, linear, mel, max_len, max_frames, n_mels,
-                    preemph, min_level_db, ref_level_db, aligned16};
+    DV3_REQUIRE(min_level_db < 0.f, "stft_mel: min_level_db must be negative (got %g)", (double)min_level_db);
+    const double inv = 1.0 / -(double)min_level_db, c2 = 20.0 * 0.30102999566398120 * inv;      // 20*log10(2) / -min_db
+    const double c0 = 1.0 - (double)ref_level_db * inv, min_level = pow(10.0, (double)min_level_db / 20.0);
+    StftParams p = {wav, lengths, mel_basis, mel_start, mel_len, linear, mel, max_len, max_frames, n_mels, preemph,
+                    (float)c2, (float)c0, (float)min_level, (float)(0.5 * c2), (float)(c0 - c2),
+                    (float)(4.0 * min_level * min_level), aligned16};
     static const cudaError_t attr = cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)sizeof(StftSmem));
     DV3_REQUIRE(attr == cudaSuccess, "stft_mel: cannot reserve %zu bytes of shared memory", sizeof(StftSmem));
