@@ -5,7 +5,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libdv3b200.so")
+LIB_PATH = os.environ.get("DV3_LIB") or os.path.join(HERE, "csrc", "libdv3b200.so")   # DV3_LIB: A/B runs of two builds
 HEADER = os.path.join(os.path.dirname(HERE), "include", "dv3b200.h")
 
 _CTYPES = {"int": ctypes.c_int, "unsigned": ctypes.c_uint, "float": ctypes.c_float,

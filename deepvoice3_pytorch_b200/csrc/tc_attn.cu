@@ -176,7 +176,34 @@ __device__ __forceinline__ void mma3(uint32_t tmain, uint32_t tcross, uint64_t a
 //   phase 1 (two stages of 64 KB):  stage s at s*65536: A hi 16 KB | A lo 16 KB | B hi 16 KB | B lo 16 KB
 //   phase 2 (aliases phase 1):      A2 hi 32 KB | A2 lo 32 KB  (2 key slabs x 128 rows x 128 B)
 //                                   B2 at 65536: per key slab [hi E*128 | lo E*128]  (<= 2 x 64 KB)
-constexpr int ROWS_SMEM = 65536 + 2 * 65536 + 1024 + 256;
+// Epilogue warps exchange 32 x 32 tiles with global memory through a per-warp transposing buffer: the thread of TMEM
+// lane r owns ROW r of the score tile, and a row of the (B,Td,Ts) probability tensors is contiguous along the keys -- a
+// direct per-thread access touches 32 different 128-byte lines per warp instruction (ncu: the softmax epilogues were
+// bound by those LSU transactions).  Through the buffer every global access is one full 128-byte line per instruction.
+constexpr int TILE_PITCH = 33;
+constexpr int TILE_FLOATS = 32 * TILE_PITCH;
+constexpr int ROWS_SMEM = 65536 + 2 * 65536 + 1024 + 256 + 4 * TILE_FLOATS * 4;
+
+// global rows [0, rows_valid) x columns [c0, c0+32) of a row-major matrix (row stride ld) starting at src -> tile
+__device__ __forceinline__ void tile_load(float* tile, const float* __restrict__ src, int ld, int rows_valid, int c0,
+                                          int ncols, int lane) {
+    __syncwarp();
+    const bool cok = c0 + lane < ncols;
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr)
+        tile[rr * TILE_PITCH + lane] = (cok && rr < rows_valid) ? __ldg(src + (size_t)rr * ld + c0 + lane) : 0.f;
+    __syncwarp();
+}
+// tile -> global rows [0, rows_valid) x columns [c0, c0+32)
+__device__ __forceinline__ void tile_store(const float* tile, float* __restrict__ dst, int ld, int rows_valid, int c0,
+                                           int ncols, int lane) {
+    __syncwarp();
+    const bool cok = c0 + lane < ncols;
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr)
+        if (cok && rr < rows_valid) dst[(size_t)rr * ld + c0 + lane] = tile[rr * TILE_PITCH + lane];
+    __syncwarp();
+}
 
 template <int BWD>
 __global__ void __launch_bounds__(AT_THREADS, 1) attn_rows_kernel(const __grid_constant__ AttnParams p) {
@@ -245,45 +272,53 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rows_kernel(const __grid_c
         const DropCfg drop = make_drop(p.p_drop, p.seed_ptr, p.salt);
         const size_t rbase = ((size_t)b * Td + (tv ? t : 0)) * Ts;
         const unsigned char* mrow = p.mask ? p.mask + (size_t)b * Ts : nullptr;
+        // this warp's 32 rows of the (B,Td,Ts) tensors, accessed through the transposing tile (see TILE_PITCH)
+        float* tile = reinterpret_cast<float*>(smem + 3 * 65536 + 256) + warp * TILE_FLOATS;
+        const int tw0 = t0 + warp * 32, rows_valid = min(max(Td - tw0, 0), 32);
+        const size_t wbase = ((size_t)b * Td + min(tw0, Td - 1)) * Ts;
         float r0v = 0.f, r1v = 0.f;      // fwd: row max, 1/sum ; bwd: dot
+        // key s is excluded (padding or beyond Ts) <=> bit (s & 31) of mb[s >> 5]: one byte load per lane and chunk
+        uint32_t mb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int s = 32 * j + lane;
+            mb[j] = __ballot_sync(0xffffffffu, s >= Ts || (mrow && mrow[s < Ts ? s : 0]));
+        }
         if (BWD == 0) {
             float mx = -INFINITY;
+#pragma unroll
             for (int c32 = 0; c32 < AT_NS; c32 += 32) {
                 float v[32];
                 tmem_ld_sum(taddr + c32, AT_NS, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int s = c32 + i;
-                    const bool ok = s < Ts && !(mrow && mrow[s]);
-                    mx = fmaxf(mx, ok ? v[i] : -INFINITY);
-                }
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((mb[c32 >> 5] >> i) & 1u) ? -INFINITY : v[i]);
             }
             float sum = 0.f;
+#pragma unroll
             for (int c32 = 0; c32 < AT_NS; c32 += 32) {
                 float v[32];
                 tmem_ld_sum(taddr + c32, AT_NS, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int s = c32 + i;
-                    const bool ok = s < Ts && !(mrow && mrow[s]);
-                    sum += ok ? expf(v[i] - mx) : 0.f;
-                }
+                for (int i = 0; i < 32; ++i) sum += ((mb[c32 >> 5] >> i) & 1u) ? 0.f : expf(v[i] - mx);
             }
             r0v = mx; r1v = 1.f / sum;
         } else {
             float dot = 0.f;
             for (int c32 = 0; c32 < AT_NS; c32 += 32) {
-                float v[32];
+                float v[32], pv[32];
                 tmem_ld_sum(taddr + c32, AT_NS, v);
-                if (!tv) continue;
+                if (c32 >= Ts) continue;                          // uniform
+                tile_load(tile, p.probs + wbase, Ts, rows_valid, c32, Ts, lane);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pv[i] = tile[lane * TILE_PITCH + i];
+                if (p.dprobs) tile_load(tile, p.dprobs + wbase, Ts, rows_valid, c32, Ts, lane);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const int s = c32 + i;
-                    if (s < Ts) {
-                        const size_t idx = rbase + s;
-                        float g = p.scale * v[i] * drop_scale(drop, (uint32_t)idx);
-                        if (p.dprobs) g += __ldg(&p.dprobs[idx]);
-                        dot = fmaf(g, __ldg(&p.probs[idx]), dot);
+                    if (tv && s < Ts) {
+                        float g = p.scale * v[i] * drop_scale(drop, (uint32_t)(rbase + s));
+                        if (p.dprobs) g += tile[lane * TILE_PITCH + i];
+                        dot = fmaf(g, pv[i], dot);
                     }
                 }
             }
@@ -293,25 +328,40 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_rows_kernel(const __grid_c
         for (int c32 = 0; c32 < AT_NS; c32 += 32) {
             float v[32], o[32];
             tmem_ld_sum(taddr + c32, AT_NS, v);
+            const bool live = c32 < Ts;                           // uniform: chunks past the last key hold nothing
+            const uint32_t mbc = c32 == 0 ? mb[0] : (c32 == 32 ? mb[1] : (c32 == 64 ? mb[2] : mb[3]));
+            float pv[32];
+            if (BWD == 1 && live) {
+                tile_load(tile, p.probs + wbase, Ts, rows_valid, c32, Ts, lane);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pv[i] = tile[lane * TILE_PITCH + i];
+                if (p.dprobs) tile_load(tile, p.dprobs + wbase, Ts, rows_valid, c32, Ts, lane);
+            }
+            float gp[32];                                         // fwd: the probability; bwd: dS
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const int s = c32 + i;
-                const size_t idx = rbase + s;
-                float a2 = 0.f;
+                float a2 = 0.f, wr = 0.f;
                 if (tv && s < Ts) {
                     if (BWD == 0) {
-                        const bool ok = !(mrow && mrow[s]);
+                        const bool ok = !((mbc >> i) & 1u);
                         const float pr = ok ? expf(v[i] - r0v) * r1v : 0.f;
-                        p.probs[idx] = pr;
-                        a2 = pr * drop_scale(drop, (uint32_t)idx);
+                        wr = pr;
+                        a2 = pr * drop_scale(drop, (uint32_t)(rbase + s));
                     } else {
-                        float g = p.scale * v[i] * drop_scale(drop, (uint32_t)idx);
-                        if (p.dprobs) g += __ldg(&p.dprobs[idx]);
-                        a2 = __ldg(&p.probs[idx]) * (g - r0v);
-                        p.ds[idx] = a2;
+                        float g = p.scale * v[i] * drop_scale(drop, (uint32_t)(rbase + s));
+                        if (p.dprobs) g += tile[lane * TILE_PITCH + i];
+                        a2 = pv[i] * (g - r0v);
+                        wr = a2;
                     }
                 }
-                o[i] = a2;
+                o[i] = a2; gp[i] = wr;
+            }
+            if (live) {
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) tile[lane * TILE_PITCH + i] = gp[i];
+                tile_store(tile, (BWD == 0 ? p.probs : p.ds) + wbase, Ts, rows_valid, c32, Ts, lane);
             }
             if (c32 < nslab * 64) {
 #pragma unroll
@@ -465,19 +515,23 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_cols_kernel(const __grid_c
     mbar_wait(&bars[0], (kchunks - 1) & 1);
     tc_fence_after();
     if (warp < 4) {
-        const int row = warp * 32 + lane, e = e0 + row;
+        // rows e of dV / dK are contiguous along the keys: through the transposing tile (the operand buffers are free)
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-        float* __restrict__ dv = p.dv + ((size_t)b * E + (e < E ? e : 0)) * Ts;
-        float* __restrict__ dk = p.dk + ((size_t)b * E + (e < E ? e : 0)) * Ts;
+        float* tile = reinterpret_cast<float*>(smem) + warp * TILE_FLOATS;
+        const int ew0 = e0 + warp * 32, rows_valid = min(max(E - ew0, 0), 32);
+        const size_t wbase = ((size_t)b * E + min(ew0, E - 1)) * Ts;
         for (int c32 = 0; c32 < AT_NS; c32 += 32) {
             float v[32], w[32];
             tmem_ld_sum(taddr + c32, 128, v);
             tmem_ld_sum(taddr + 256 + c32, 128, w);
-            if (e < E) {
+            if (c32 >= Ts) continue;                              // uniform
+            __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c32 + i < Ts) { dv[c32 + i] = p.scale * v[i]; dk[c32 + i] = w[i]; }
-            }
+            for (int i = 0; i < 32; ++i) tile[lane * TILE_PITCH + i] = p.scale * v[i];
+            tile_store(tile, p.dv + wbase, Ts, rows_valid, c32, Ts, lane);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tile[lane * TILE_PITCH + i] = w[i];
+            tile_store(tile, p.dk + wbase, Ts, rows_valid, c32, Ts, lane);
         }
     }
     tc_fence_before();
