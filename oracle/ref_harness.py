@@ -160,6 +160,36 @@ def load_train(which="b200", root=None):
     return m
 
 
+class CharFrontend:
+    """Stand-in for ``deepvoice3_pytorch.frontend.en`` (nltk / CMU dictionary are not installed): one id per
+    character, ids in [2, N_VOCAB) like the reference's symbol table, 1 = end of sentence."""
+    n_vocab = N_VOCAB
+
+    @staticmethod
+    def text_to_sequence(text, p=0.0):
+        return [2 + (ord(c) * 7) % (N_VOCAB - 2) for c in text] + [1]
+
+
+def load_synthesis(which="b200", audio_module=None, root=None):
+    """Execute the reference's synthesis.py (module level only) bound to the chosen package.  ``audio_module`` is what
+    its ``import audio`` resolves to: this package's ``audio`` for "b200"; for "reference" a shim must be passed (the
+    reference's audio.py needs the uninstalled ``lws`` for the inverse path).  ``tts()`` is then callable unchanged."""
+    root = root or ref_root()
+    if root is None:
+        raise RuntimeError("no reference tree: run `python oracle/make_ref.py` in the build container")
+    pkg = bind_package(which, root)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    for k in ("hparams", "audio"):
+        sys.modules.pop(k, None)
+    if audio_module is not None:
+        sys.modules["audio"] = audio_module
+    m = _load_file("dv3_ref_synthesis_" + which, os.path.join(root, "synthesis.py"))
+    m._frontend = CharFrontend
+    m._package = pkg
+    return m
+
+
 def apply_preset(tr, name, **overrides):
     """hparams.parse_json(presets/<name>.json) (train.py:936-939) + keyword overrides."""
     with open(os.path.join(ref_root(), "presets", name + ".json")) as f:

@@ -3,6 +3,8 @@ oracle/ref_harness.py, which only stands in for uninstalled CLI / logging / text
 ``deepvoice3_pytorch_b200`` -- ``build_model()``, ``collate_fn`` and the ``train()`` loop with ``model(...)``,
 ``loss.backward()``, ``clip_grad_norm_`` and ``torch.optim.Adam`` -- and produces the same losses as the same file on
 the reference package."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -74,3 +76,55 @@ def test_reference_train_loop_runs_unchanged_on_this_package(preset, n_speakers,
         np.testing.assert_allclose(got[0], ref[0], rtol=2e-4, err_msg=tag + " (first step: identical weights)")
         np.testing.assert_allclose(got, ref, rtol=5e-3, err_msg=tag)
     assert all(np.isfinite(v) for _, v in logs["b200"]["loss"])
+
+
+@pytest.mark.gpu
+def test_reference_synthesis_tts_runs_unchanged_on_this_package():
+    """The inference-side caller: reference ``synthesis.py:tts()`` (text ids -> ``model(...)`` autoregressive decoding
+    -> ``audio._denormalize`` / ``audio.inv_spectrogram``) executed UNCHANGED with this package's model and ``audio``
+    module, against the same function on the reference package (PyTorch eager on the same GPU; its waveform step uses
+    the numpy restatement of audio.py because ``lws`` is not installed).  Same weights, a decoder that never raises the
+    done flag early, 24 decoder steps: mel / linear / alignment agree; both waveforms are finite and of the length
+    the frame count implies."""
+    import types
+    H = _harness()
+    if not os.path.exists(os.path.join(H.ref_root(), "synthesis.py")):
+        pytest.skip("oracle/_ref predates synthesis.py (re-run oracle/make_ref.py)")
+    from oracle import audio_oracle as A
+    from deepvoice3_pytorch_b200 import audio as our_audio
+    shim = types.ModuleType("audio")                       # what the reference side's `import audio` resolves to
+    shim._denormalize = lambda S: np.clip(S, 0, 1) * 100.0 - 100.0
+    shim.inv_spectrogram = lambda S: A.inv_spectrogram(S, n_iter=4)
+    old_iters = our_audio.hparams.griffin_lim_iters
+    our_audio.hparams.griffin_lim_iters = 4
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                # the reference side: exact fp32 convolutions
+    outs, sd = {}, None
+    try:
+        for which, aud in (("reference", shim), ("b200", our_audio)):
+            syn = H.load_synthesis(which, aud)
+            tr = H.load_train(which)
+            H.apply_preset(tr, "deepvoice3_ljspeech")
+            torch.manual_seed(0)
+            model = tr.build_model()
+            if sd is None:
+                sd = {k: v.clone() for k, v in model.state_dict().items()}
+                sd["seq2seq.decoder.fc.bias"] = torch.full_like(sd["seq2seq.decoder.fc.bias"], -8.0)   # never "done"
+            model.load_state_dict(sd)
+            model.seq2seq.decoder.max_decoder_steps = 24
+            waveform, alignment, spectrogram, mel = syn.tts(model, "hello b200", p=0, speaker_id=None, fast=True)
+            outs[which] = (np.asarray(waveform), np.asarray(alignment), np.asarray(spectrogram), np.asarray(mel))
+    finally:
+        our_audio.hparams.griffin_lim_iters = old_iters
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    ref, got = outs["reference"], outs["b200"]
+    assert type(model).__module__.startswith("deepvoice3_pytorch_b200")
+    for name, r, g in zip(("alignment", "spectrogram", "mel"), ref[1:], got[1:]):
+        assert r.shape == g.shape, name
+        scale = max(1.0, float(np.abs(r).max()))
+        np.testing.assert_allclose(g, r, rtol=2e-3, atol=2e-3 * scale, err_msg=name)
+    T = ref[2].shape[0]
+    assert got[2].shape == (T, 513) and got[3].shape[1] == 80
+    n = our_audio.inv_num_samples(T)
+    assert got[0].shape == (n,) and np.isfinite(got[0]).all() and np.abs(got[0]).max() > 0
+    assert ref[0].shape[0] == n and np.isfinite(ref[0]).all()
