@@ -77,6 +77,48 @@ def _device_basis(device):
     return _basis_cache[key]
 
 
+def load_wav(path):
+    """float32 mono waveform in [-1, 1] at ``hparams.sample_rate`` -- reference audio.py:12-13
+    (``librosa.core.load(path, sr=hparams.sample_rate)[0]``).  Host-side file plumbing (scipy): integer PCM is scaled by
+    its full range, channels are averaged, and a file at another rate is resampled with a polyphase filter (librosa
+    uses resampy's kaiser_best; identical output only when the rates already agree, as for the reference's datasets)."""
+    from scipy.io import wavfile
+    sr, x = wavfile.read(path)
+    if np.issubdtype(x.dtype, np.integer):
+        x = x.astype(np.float32) / float(2 ** (8 * x.dtype.itemsize - 1)) if x.dtype != np.uint8 \
+            else (x.astype(np.float32) - 128.0) / 128.0
+    else:
+        x = x.astype(np.float32)
+    if x.ndim > 1:
+        x = x.mean(axis=1)
+    if sr != hparams.sample_rate:
+        from math import gcd
+        from scipy.signal import resample_poly
+        g = gcd(int(sr), int(hparams.sample_rate))
+        x = resample_poly(x, hparams.sample_rate // g, sr // g).astype(np.float32)
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def save_wav(wav, path):
+    """16-bit PCM at ``hparams.sample_rate``, peak-normalised exactly like reference audio.py:16-18."""
+    from scipy.io import wavfile
+    wav = np.asarray(wav, dtype=np.float64)
+    wav = wav * 32767 / max(0.01, np.max(np.abs(wav)))
+    wavfile.write(path, hparams.sample_rate, wav.astype(np.int16))
+
+
+def preemphasis(x):
+    """y[n] = x[n] - c*x[n-1] on the host (reference audio.py:21-23, ``lfilter([1, -c], [1], x)``); the fused kernel
+    applies the same filter on the fly, this function exists for callers that want the signal itself."""
+    from scipy import signal
+    return signal.lfilter([1, -hparams.preemphasis], [1], np.asarray(x))
+
+
+def _linear_to_mel(spectrogram):
+    """mel_basis @ |S| -- reference audio.py:64-68 (host-side helper; the kernel fuses it)."""
+    return np.dot(_build_mel_basis(), spectrogram)
+
+
 def num_frames(n_samples):
     return lib.raw("dv3_stft_num_frames")(int(n_samples))
 
@@ -176,7 +218,10 @@ def griffin_lim(mag, n_iter=None):
 
 
 def inv_preemphasis(x):
-    """y[n] = x[n] + c*y[n-1] -- reference audio.py:26-28.  x: (n,) or (nclips, n) fp32 CUDA tensor."""
+    """y[n] = x[n] + c*y[n-1] -- reference audio.py:26-28.  x: (n,) or (nclips, n) fp32 CUDA tensor -> tensor; a numpy
+    array (the reference's calling convention) is moved to the GPU and a numpy array comes back."""
+    if not torch.is_tensor(x):
+        return inv_preemphasis(torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).cuda()).cpu().numpy()
     x2 = x.view(1, -1) if x.dim() == 1 else x
     x2 = x2.contiguous()
     y = torch.empty_like(x2)

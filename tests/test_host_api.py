@@ -203,3 +203,27 @@ def test_hparams_mapping_matches_the_bench_presets():
     model = hparams.build_model(dict(presets["nyanko_ljspeech"], encoder_channels=32, decoder_channels=32,
                                      converter_channels=32, text_embed_dim=16), n_vocab=149)
     assert model.seq2seq.decoder.in_dim == 80 and model.linear_dim == 513
+
+
+def test_audio_file_helpers_round_trip(tmp_path):
+    """audio.load_wav / save_wav / preemphasis / _linear_to_mel: the host-side helpers of reference audio.py:12-23,64-68
+    (scipy only).  save -> load reproduces the peak-normalised 16-bit signal; a file at another rate is resampled to
+    hparams.sample_rate; preemphasis matches the oracle's restatement."""
+    from deepvoice3_pytorch_b200 import audio
+    from oracle import audio_oracle as A
+    from scipy.io import wavfile
+    rng = np.random.RandomState(0)
+    x = (0.3 * rng.randn(4000)).astype(np.float32)
+    p = str(tmp_path / "a.wav")
+    audio.save_wav(x, p)
+    sr, raw = wavfile.read(p)
+    assert sr == audio.hparams.sample_rate and raw.dtype == np.int16 and abs(int(np.abs(raw).max()) - 32767) <= 1
+    y = audio.load_wav(p)
+    assert y.dtype == np.float32 and y.shape == x.shape
+    np.testing.assert_allclose(y, x / np.abs(x).max() * (32767 / 32768.0), atol=1.0 / 32768)
+    wavfile.write(str(tmp_path / "b.wav"), 44100, np.stack([raw, raw], axis=1).repeat(2, axis=0)[:8000])   # stereo, 2x rate
+    z = audio.load_wav(str(tmp_path / "b.wav"))
+    assert z.ndim == 1 and abs(len(z) - 4000) <= 1
+    np.testing.assert_allclose(audio.preemphasis(x), A.preemphasis(x.astype(np.float64)), atol=1e-6)
+    S = np.abs(rng.randn(513, 7)).astype(np.float32)
+    np.testing.assert_allclose(audio._linear_to_mel(S), A.mel_basis() @ S, rtol=1e-5, atol=1e-7)
