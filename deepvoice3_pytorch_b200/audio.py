@@ -27,6 +27,9 @@ class _HP:
     ref_level_db = 20
     power = 1.4                   # spectrogram sharpening before phase recovery (presets/*.json)
     griffin_lim_iters = 60
+    rescaling = False             # preprocess.py: y = x / |x|.max() * rescaling_max (hparams.py:46-48)
+    rescaling_max = 0.999
+    min_text = 20                 # utterances with shorter transcripts are skipped (hparams.py:137)
 
 
 hparams = _HP()

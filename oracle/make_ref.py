@@ -4,7 +4,7 @@
     python oracle/make_ref.py            (build container only: needs /root/reference)
 
 The reference is pure Python, so "building" it is: copy the package and the four top-level modules ``train.py``
-imports (``train.py``, ``hparams.py``, ``lrschedule.py``, ``audio.py``), ``synthesis.py`` and ``presets/`` from where they lie under
+imports (``train.py``, ``hparams.py``, ``lrschedule.py``, ``audio.py``), ``synthesis.py``, ``ljspeech.py`` and ``presets/`` from where they lie under
 /root/reference into ``oracle/_ref/`` and generate ``deepvoice3_pytorch/version.py`` the way ``setup.py:33-39`` does.
 ``oracle/_ref/`` is git-ignored (no reference source enters the history) but NOT gpurun-ignored, so it travels to
 the GPU box, where /root/reference does not exist.  Consumers (all test / bench side, never the product package):
@@ -22,7 +22,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DST = os.path.join(HERE, "_ref")
-FILES = ["train.py", "hparams.py", "lrschedule.py", "audio.py", "synthesis.py"]
+FILES = ["train.py", "hparams.py", "lrschedule.py", "audio.py", "synthesis.py", "ljspeech.py"]
 
 
 def build(ref="/root/reference", quiet=False):

@@ -190,6 +190,20 @@ def load_synthesis(which="b200", audio_module=None, root=None):
     return m
 
 
+def load_ljspeech(audio_module, root=None):
+    """Execute the reference's ljspeech.py (the LJSpeech preprocessor: ``build_from_path`` / ``_process_utterance``)
+    with ``import audio`` resolving to ``audio_module`` and ``hparams`` to the reference's own hparams.py."""
+    root = root or ref_root()
+    if root is None:
+        raise RuntimeError("no reference tree: run `python oracle/make_ref.py` in the build container")
+    bind_package("b200", root)                             # hparams.py needs the vendored tfcompat.hparam only
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    sys.modules.pop("hparams", None)
+    sys.modules["audio"] = audio_module
+    return _load_file("dv3_ref_ljspeech", os.path.join(root, "ljspeech.py"))
+
+
 def apply_preset(tr, name, **overrides):
     """hparams.parse_json(presets/<name>.json) (train.py:936-939) + keyword overrides."""
     with open(os.path.join(ref_root(), "presets", name + ".json")) as f:

@@ -128,3 +128,51 @@ def test_reference_synthesis_tts_runs_unchanged_on_this_package():
     n = our_audio.inv_num_samples(T)
     assert got[0].shape == (n,) and np.isfinite(got[0]).all() and np.abs(got[0]).max() > 0
     assert ref[0].shape[0] == n and np.isfinite(ref[0]).all()
+
+
+@pytest.mark.gpu
+def test_reference_ljspeech_preprocessor_and_batched_equivalent(tmp_path):
+    """The caller of the audio front-end: reference ``ljspeech.py:_process_utterance`` (load_wav -> spectrogram ->
+    melspectrogram -> np.save, :40-79) runs UNCHANGED on this package's ``audio`` module, one clip per launch; the
+    batched ``preprocess.build_from_path`` (same arguments, one fused launch per batch) writes bit-identical files and
+    returns the same ``train.txt`` rows, including the reference's skip of short transcripts."""
+    from scipy.io import wavfile
+    H = _harness()
+    if not os.path.exists(os.path.join(H.ref_root(), "ljspeech.py")):
+        pytest.skip("oracle/_ref predates ljspeech.py (re-run oracle/make_ref.py)")
+    from oracle import audio_oracle as A
+    from deepvoice3_pytorch_b200 import audio, preprocess
+    in_dir, out_a, out_b = tmp_path / "in", tmp_path / "ref", tmp_path / "ours"
+    (in_dir / "wavs").mkdir(parents=True)
+    out_a.mkdir(); out_b.mkdir()
+    lens = [30001, 22050, 5000, 47777, 12345]
+    texts = ["the quick brown fox jumps over the lazy dog %d" % i for i in range(5)]
+    texts[2] = "too short"                                  # < hparams.min_text = 20: skipped by both
+    with open(in_dir / "metadata.csv", "w", encoding="utf-8") as f:
+        for i, (n, t) in enumerate(zip(lens, texts)):
+            x = A.synthetic_clip(70 + i, n=n)
+            wavfile.write(str(in_dir / "wavs" / ("LJ%03d.wav" % i)), 22050, (x * 32767).astype(np.int16))
+            f.write("LJ%03d|%s|%s\n" % (i, t, t))
+    lj = H.load_ljspeech(audio)
+    assert lj.hparams.min_text == audio.hparams.min_text and not lj.hparams.rescaling
+    rows_ref, index = [], 1
+    for i, t in enumerate(texts):
+        if len(t) < lj.hparams.min_text:
+            continue
+        rows_ref.append(lj._process_utterance(str(out_a), index, str(in_dir / "wavs" / ("LJ%03d.wav" % i)), t))
+        index += 1
+    rows = preprocess.build_from_path(str(in_dir), str(out_b), num_workers=2, batch_clips=3)
+    assert rows == rows_ref and len(rows) == 4
+    for spec_name, mel_name, n_frames, _ in rows:
+        a, b = np.load(out_a / spec_name), np.load(out_b / spec_name)
+        assert a.shape == (n_frames, 513) and a.dtype == np.float32 and np.array_equal(a, b)
+        a, b = np.load(out_a / mel_name), np.load(out_b / mel_name)
+        assert a.shape == (n_frames, 80) and np.array_equal(a, b)
+    frames, hours = preprocess.write_metadata(rows, str(out_b))
+    lines = open(out_b / "train.txt", encoding="utf-8").read().splitlines()
+    assert len(lines) == 4 and lines[0].split("|")[:3] == ["ljspeech-spec-00001.npy", "ljspeech-mel-00001.npy",
+                                                           str(rows[0][2])] and frames == sum(r[2] for r in rows)
+    # and against the numpy restatement of audio.py for one utterance
+    ref_lin, ref_mel = A.process_utterance(audio.load_wav(str(in_dir / "wavs" / "LJ000.wav")))
+    got = np.load(out_b / rows[0][0])
+    assert got.shape == ref_lin.shape and np.abs(got - ref_lin).mean() < 2e-4
