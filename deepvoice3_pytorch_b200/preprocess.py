@@ -48,10 +48,20 @@ def spectrograms_batch(wavs):
     return out
 
 
-def build_from_path(in_dir, out_dir, num_workers=1, tqdm=lambda x: x, batch_clips=64, name="ljspeech"):
+def build_from_path(in_dir, out_dir, num_workers=1, tqdm=lambda x: x, batch_clips=64, name="ljspeech",
+                    rank=None, world=None):
     """Same contract as reference ``ljspeech.build_from_path`` (:9-37): reads ``in_dir/metadata.csv`` and
     ``in_dir/wavs/*.wav``, writes the .npy pairs into ``out_dir`` and returns
-    ``[(spectrogram_filename, mel_filename, n_frames, text)]`` in file order."""
+    ``[(spectrogram_filename, mel_filename, n_frames, text)]`` in file order.
+
+    Multi-GPU (one process per GPU): utterances are dealt round-robin over the ranks -- the work is independent per
+    clip, so there is no data-path collective; file indices are global, every rank writes its own files, and the rows of
+    all ranks are merged into file order with one ``all_gather_object`` of the (tiny) row lists.  ``rank`` / ``world``
+    default to the initialised ``torch.distributed`` group, else to a single process."""
+    import torch.distributed as dist
+    if world is None:
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
     hp = audio.hparams
     items = []
     index = 1
@@ -63,6 +73,7 @@ def build_from_path(in_dir, out_dir, num_workers=1, tqdm=lambda x: x, batch_clip
                 continue
             items.append((index, os.path.join(in_dir, "wavs", "%s.wav" % parts[0]), text))
             index += 1
+    items = items[rank::world]                       # this rank's share; indices stay global
     rows = []
     with ThreadPoolExecutor(max_workers=max(1, num_workers)) as pool:
         batches = [items[i:i + batch_clips] for i in range(0, len(items), batch_clips)]
@@ -76,10 +87,14 @@ def build_from_path(in_dir, out_dir, num_workers=1, tqdm=lambda x: x, batch_clip
                 spec_name, mel_name = "%s-spec-%05d.npy" % (name, idx), "%s-mel-%05d.npy" % (name, idx)
                 saves.append(pool.submit(np.save, os.path.join(out_dir, spec_name), lin, allow_pickle=False))
                 saves.append(pool.submit(np.save, os.path.join(out_dir, mel_name), mel, allow_pickle=False))
-                rows.append((spec_name, mel_name, lin.shape[0], text))
+                rows.append((idx, (spec_name, mel_name, lin.shape[0], text)))
         for s in saves:
             s.result()
-    return rows
+    if world > 1 and dist.is_available() and dist.is_initialized():
+        parts = [None] * world
+        dist.all_gather_object(parts, rows)
+        rows = [r for part in parts for r in part]
+    return [r for _, r in sorted(rows, key=lambda ir: ir[0])]
 
 
 def write_metadata(metadata, out_dir):
