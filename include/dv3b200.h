@@ -153,7 +153,9 @@ int dv3_adam_clip(float* p, const float* g, float* m, float* v, long long n, con
  * mel_basis (n_mels, 513) dense with mel_start/mel_len [n_mels] giving each filter's non-zero span;
  * linear (nclips, max_frames, 513) and mel (nclips, max_frames, n_mels) -- the transposed (T, F) layout the
  * preprocessors store (ljspeech.py:72-73); either output may be NULL.  Frames >= a clip's own count are zero-filled (outputs need no
- * initialisation); n_mels <= 128. */
+ * initialisation); n_mels <= 128; min_level_db < 0.  Fastest when wav is 16-byte aligned and max_len % 4 == 0 (bulk /
+ * 16-byte staging copies; any other pitch works through 4-byte copies, bit-identical results).  The first call on a
+ * device builds a 2.7 KB table with a one-off kernel on the given stream (synchronised unless the stream is capturing). */
 int dv3_stft_num_frames(int n_samples);
 int dv3_stft_mel(const float* wav, const int* lengths, const float* mel_basis, const int* mel_start,
                  const int* mel_len, float* linear, float* mel, int nclips, int max_len, int max_frames,
